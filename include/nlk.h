@@ -1,0 +1,187 @@
+/* nlk.h -- C-ABI of the B200-native exptA hot path (neklab drop-in boundary).
+ *
+ * Every entry point is what a Fortran ISO_C_BINDING shim of neklab would bind for this
+ * path.  For each group the reference interface it replaces is cited
+ * as file:line under /root/reference.  All functions return 0 on success, non-zero on
+ * error (message via nlk_last_error()); the reference aborts (`type_error`/`nek_stop_error`,
+ * src/neklab_nek_setup.f90:406-417) where we return a status.
+ *
+ * Layout conventions: host arrays are double, element-major, x (r) fastest, exactly Nek's
+ * (lx1,ly1,lz1,lelv) / (lx2,ly2,lz2,lelv) column-major storage.  Vectors/operators are opaque
+ * handles owning device (HBM) buffers.  One host thread per nlk_ctx; not re-entrant (same as
+ * the reference's COMMON-block state).  There is NO CPU fallback: any entry point that needs
+ * the device fails with an error if no CUDA device is usable.
+ */
+#ifndef NLK_H
+#define NLK_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nlk_mesh nlk_mesh;   /* host-side geometry + numbering (Nek setup: geom1/geom2/set_vert) */
+typedef struct nlk_ctx nlk_ctx;     /* device-resident solver state (Nek COMMON blocks)                  */
+typedef struct nlk_vec nlk_vec;     /* nek_dvector          src/vectors/neklab_vectors.f90:26-50         */
+typedef struct nlk_op nlk_op;       /* exptA_linop          src/linops/neklab_linops.f90:35-44           */
+
+const char* nlk_last_error(void);
+int nlk_version(void);
+
+/* ------------------------------------------------------------------ mesh (host only; no GPU needed)
+ * Replaces what Nek5000 derives from SIZE + .re2/.ma2 at start-up (un-vendored);
+ * the in-tree consumers are bm1/vmult/v?mask/glo_num users in src/vectors/real_vectors.f90:100-113,208-233. */
+typedef struct {
+  int32_t ndim;            /* ldim                                   SIZE:12 */
+  int32_t lx1;             /* GLL points per direction               SIZE:13 */
+  int32_t lxd;             /* dealiasing GL points                   SIZE:14 */
+  int64_t nelg;            /* global element count                   SIZE:16 */
+  int64_t nel;             /* local element count (== nelg if gllnid==NULL) */
+  const double* xm1;       /* [nel][lx1^ndim] local GLL coordinates */
+  const double* ym1;
+  const double* zm1;       /* NULL in 2-D */
+  const int64_t* vertex;   /* [nelg][2^ndim] .ma2 global vertex ids, lexicographic corners, ALL elements */
+  const char* cbc_v;       /* [nel][2*ndim][3] velocity boundary codes (preprocessor face order)  */
+  const char* cbc_t;       /* [nel][2*ndim][3] temperature codes, or NULL */
+  const int32_t* gllnid;   /* [nelg] owning rank of every element (Nek gllnid), or NULL = single rank */
+  int32_t rank, nranks;
+} nlk_mesh_desc;
+
+typedef struct {
+  int32_t ndim, lx1, lx2, lxd;
+  int64_t nel, nelg;
+  int64_t np1, np2;        /* points per element on mesh 1 / mesh 2 */
+  int64_t nglob_local;     /* distinct global nodes touching this rank */
+  int64_t nshared_local;   /* distinct global nodes with >1 local copies */
+  int64_t nvert;           /* global vertex count */
+  int32_t has_outflow;     /* pressure operator non-singular */
+  int32_t nneigh;          /* neighbour ranks in the gather-scatter exchange */
+  double volvm1, volvm2;   /* local sums of bm1 / bm2 */
+} nlk_mesh_info_t;
+
+int nlk_partition(const int64_t* pid, int64_t nelg, int32_t nranks, int32_t* gllnid); /* Nek power-of-two rule on .ma2 leaf ids */
+int nlk_mesh_create(const nlk_mesh_desc* d, nlk_mesh** out);
+int nlk_mesh_destroy(nlk_mesh* m);
+int nlk_mesh_info(const nlk_mesh* m, nlk_mesh_info_t* out);
+int nlk_mesh_glo_num(const nlk_mesh* m, int64_t* glo /* [nel][np1], 1-based */);
+/* name in: bm1 jac binvm1 vmult vmask0..2 tmask bm2 g11 g12 g13 g22 g23 g33 (mesh-1 sized, bm2 mesh-2 sized) */
+int nlk_mesh_field(const nlk_mesh* m, const char* name, double* out);
+/* gather-scatter exchange plan with neighbour rank index k (0..nneigh-1): rank id, count, global node ids (sorted) */
+int nlk_mesh_neighbor(const nlk_mesh* m, int32_t k, int32_t* rank, int64_t* count, int64_t* gids /* may be NULL */);
+/* 1-D operators: name in z1 w1 z2 w2 zd wd D I12 D12 I1d Dd ; returns count written */
+int nlk_mesh_basis(const nlk_mesh* m, const char* name, double* out, int64_t cap);
+
+/* ------------------------------------------------------------------ small dense host kernels (LAPACK-free)
+ * replaces LightKrylov's `eig`/`schur` calls through stdlib_linalg (src/neklab_otd.f90:229,248). */
+int nlk_dense_eig(int32_t n, const double* A /* row-major n*n */, double* wr, double* wi,
+                  double* VR /* n*n row-major; complex pairs stored LAPACK dgeev style in columns */);
+
+/* ------------------------------------------------------------------ solver context (device)
+ * replaces Nek's param()/COMMON state poked by setup_nek (src/neklab_nek_setup.f90:39-247). */
+typedef struct {
+  double viscosity;        /* param(2): h1 = 1/Re                      .par [VELOCITY] viscosity */
+  double density;          /* param(1)                                 .par [VELOCITY] density   */
+  int32_t torder;          /* |param(27)|, 1..3                        .par timeStepper          */
+  double vtol;             /* param(22) -> TOLHDF   src/neklab_nek_setup.f90:228 */
+  double ptol;             /* param(21) -> TOLPDF   src/neklab_nek_setup.f90:227 */
+  int32_t ifheat;          /* temperature coupled (exptA_temp_linop)   */
+  double conductivity, rhocp, ttol;
+  double buoyancy[3];      /* f_c += buoyancy[c]*T'  (examples/rayBen/baseflow/rayBen.usr:75-105) */
+  double filter_weight;    /* param(103)            .par filterWeight */
+  double filter_cutoff;    /* filterCutoffRatio */
+  int32_t cg_maxit;        /* Helmholtz CG cap */
+  int32_t gmres_maxit;     /* Nek: 100 */
+  int32_t lgmres;          /* SIZE lgmres = 30 */
+  int32_t precond;         /* 0 = mass-scaled identity, 1 = Schwarz + coarse (semg_xxt analogue) */
+  int32_t pr_proj;         /* residualProj: size of the pressure projection space (0 = off, Nek mxprev=20) */
+  double cfl_limit;        /* 0.5 for the linear solver (src/linops/exponential_propagator.f90:12) */
+} nlk_params;
+
+int nlk_params_default(nlk_params* p);
+int nlk_ctx_create(const nlk_mesh* m, const nlk_params* p, int32_t device, nlk_ctx** out);
+int nlk_ctx_destroy(nlk_ctx* c);
+int nlk_ctx_set_tol(nlk_ctx* c, double vtol, double ptol);           /* setup_nek vtol/ptol args */
+/* multi-rank: attach an NCCL communicator built from a broadcast unique id (128 bytes) */
+int nlk_comm_unique_id(char id[128]);
+int nlk_ctx_comm_init(nlk_ctx* c, const char id[128], int32_t rank, int32_t nranks);
+int nlk_ctx_sync(nlk_ctx* c);                                        /* stream synchronize */
+void* nlk_ctx_stream(nlk_ctx* c);                                    /* cudaStream_t */
+
+/* ------------------------------------------------------------------ nek_dvector
+ * src/vectors/neklab_vectors.f90:64-113 (TBP interfaces), src/vectors/real_vectors.f90 (bodies). */
+int nlk_vec_create(nlk_ctx* c, nlk_vec** out);
+int nlk_vec_destroy(nlk_vec* v);
+int nlk_vec_copy(nlk_vec* dst, const nlk_vec* src);                  /* Fortran assignment / allocate(source=) */
+int nlk_vec_zero(nlk_vec* v);                                        /* nek_dzero  real_vectors.f90:37-50   */
+int nlk_vec_rand(nlk_vec* v, int32_t ifnorm, uint64_t seed);         /* nek_drand  :52-123 (seeded, C0, BC-satisfying) */
+int nlk_vec_scal(nlk_vec* v, double alpha);                          /* nek_dscal  :125-160 */
+int nlk_vec_axpby(double alpha, const nlk_vec* x, double beta, nlk_vec* self); /* nek_daxpby :162-206: self = alpha*x + beta*self (+rst quirk) */
+int nlk_vec_dot(const nlk_vec* self, const nlk_vec* x, double* out); /* nek_ddot   :208-233 (bm1-weighted, no pressure) */
+int nlk_vec_norm(const nlk_vec* self, double* out);
+int nlk_vec_size(const nlk_vec* v, int64_t* n);                      /* nek_dsize  :235-247 */
+int nlk_vec_save_rst(nlk_vec* self, const nlk_vec* state, int32_t irst); /* dsave_rst :249-291 */
+int nlk_vec_get_rst(const nlk_vec* self, nlk_vec* out, int32_t irst);    /* dget_rst  :293-333 */
+int nlk_vec_nrst(const nlk_vec* v, int32_t* nrst);                   /* dhas_rst_fields :335-338 */
+int nlk_vec_clear_rst(nlk_vec* v);                                   /* dclear_rst_fields :340-346 */
+/* nek2vec / vec2nek (src/neklab_utils.f90:84-134): host <-> device marshalling; NULL pointers are skipped */
+int nlk_vec_upload(nlk_vec* v, const double* vx, const double* vy, const double* vz, const double* pr, const double* theta);
+int nlk_vec_download(const nlk_vec* v, double* vx, double* vy, double* vz, double* pr, double* theta);
+
+/* block kernels replacing LightKrylov innerprod / linear_combination / double_gram_schmidt_step */
+int nlk_basis_innerprod(nlk_vec* const* X, int32_t k, const nlk_vec* y, double* h);
+int nlk_basis_axpy(nlk_vec* y, nlk_vec* const* X, int32_t k, const double* c);   /* y += X c (current fields; rst per quirk) */
+int nlk_basis_dgs(nlk_vec* y, nlk_vec* const* X, int32_t k, double* h, double* norm_out);
+
+/* ------------------------------------------------------------------ exptA_linop
+ * src/linops/neklab_linops.f90:35-75 ; src/linops/exponential_propagator.f90 (init :4-13, matvec :15-60,
+ * rmatvec :62-107, compute_rst :109-127, get_rst :129-142); exptA_temp_linop: exponential_propagator_temp.f90. */
+typedef struct {
+  int32_t nsteps;
+  double dt;
+  int64_t cg_iters, gmres_iters, steps, matvecs;
+  double ms_total;         /* device time of the last matvec (CUDA events) */
+  int64_t launches;        /* kernel launches issued by the last matvec */
+} nlk_stats;
+
+int nlk_exptA_create(nlk_ctx* c, double tau, const nlk_vec* baseflow, nlk_op** out);
+int nlk_exptA_destroy(nlk_op* op);
+int nlk_exptA_init(nlk_op* op);
+int nlk_exptA_set_tau(nlk_op* op, double tau);                        /* apply_exptA :224-266 */
+int nlk_exptA_matvec(nlk_op* op, const nlk_vec* in, nlk_vec* out);
+int nlk_exptA_rmatvec(nlk_op* op, const nlk_vec* in, nlk_vec* out);
+int nlk_exptA_stats(const nlk_op* op, nlk_stats* out);
+/* neklab_forcing registry (src/neklab_nek_forcing.f90:57-114): constant body force added to the perturbation rhs */
+int nlk_ctx_set_forcing(nlk_ctx* c, const double* fx, const double* fy, const double* fz);
+
+/* ------------------------------------------------------------------ analysis entry points (device-resident bases)
+ * src/neklab_analysis.f90:38-105 (eigs), :107-156 (svds), :158-212 (newton/gmres). */
+typedef void (*nlk_eigs_cb)(int32_t iter, int32_t k, const double* lam_re, const double* lam_im,
+                            const double* resid, void* user);
+int nlk_eigs(nlk_op* op, int32_t nev, int32_t kdim, double tol, int32_t transpose, const nlk_vec* x0,
+             double* lam_re, double* lam_im, double* resid, nlk_vec** eigvecs /* 2*nev (re,im) or NULL */,
+             int32_t* niter, nlk_eigs_cb cb, void* user, int32_t* info);
+int nlk_svds(nlk_op* op, int32_t nsv, int32_t kdim, double tol, const nlk_vec* x0, double* sigma, double* resid,
+             nlk_vec** U, nlk_vec** V, int32_t* niter, int32_t* info);
+int nlk_gmres(nlk_op* op, int32_t minus_identity, const nlk_vec* b, nlk_vec* x, int32_t kdim, double atol, double rtol,
+              int32_t maxiter, int32_t transpose, int32_t* info);
+
+/* ------------------------------------------------------------------ kernel-level test/bench hooks
+ * (the K-numbered kernels of SURVEY §2.3; host arrays in, host arrays out unless noted) */
+int nlk_test_axhelm(nlk_ctx* c, const double* u, double h1, double h2, double* w);          /* K1, local (no dssum) */
+int nlk_test_dssum(nlk_ctx* c, double* u);                                                   /* K2 */
+int nlk_test_opdiv(nlk_ctx* c, const double* ux, const double* uy, const double* uz, double* p);   /* K5 */
+int nlk_test_opgradt(nlk_ctx* c, const double* p, double* wx, double* wy, double* wz);       /* K5 */
+int nlk_test_cdabdtp(nlk_ctx* c, const double* p, double* ep);                               /* K6 */
+int nlk_test_convect(nlk_ctx* c, const double* u, const double* cx, const double* cy, const double* cz, double* out); /* K3 */
+int nlk_test_convect_adj(nlk_ctx* c, const double* const* U, const double* const* cf, double* const* out);            /* K4 */
+int nlk_test_helmholtz(nlk_ctx* c, const double* f, double h1, double h2, int32_t comp, double tol, double* x, int32_t* iters); /* K8 */
+int nlk_test_pressure(nlk_ctx* c, const double* rhs, double tol, double* x, int32_t* iters); /* K9-K11 */
+int nlk_test_precond(nlk_ctx* c, const double* r, double* z);                                /* K10/K11 */
+int nlk_test_cfl(nlk_ctx* c, const double* ux, const double* uy, const double* uz, double dt, double* cfl); /* K14 */
+/* time a device-resident kernel nrep times on the ctx stream with CUDA events; returns mean ms per launch.
+ * which: 0 axhelm, 1 dssum, 2 cdabdtp, 3 convect(all comps), 4 precond, 5 vec dot, 6 cg iteration */
+int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_launch, double* algo_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,618 @@
+// C-ABI: context life-cycle (uploads + device-side setup), nek_dvector operations, exptA operator, test hooks.
+// Reference interfaces replaced: see include/nlk.h (file:line citations per entry point).
+#include "nlk_ctx.hpp"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+using namespace nlk;
+
+namespace nlk {
+static int check_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { set_error("no usable CUDA device: libnlk has no CPU fallback"); return 1; }
+  return 0;
+}
+
+// upload everything the kernels need and run the device-side parts of the setup (dssum-dependent quantities)
+static int ctx_setup(nlk_ctx* c) {
+  const HostMesh& hm = c->mesh->hm; DevMesh& dm = c->dm; const Basis& b = hm.b;
+  const int d = hm.ndim, n = hm.n, q = hm.q, m = hm.m;
+  dm.ndim = d; dm.n = n; dm.m = m; dm.q = q; dm.np1 = hm.np1; dm.np2 = hm.np2; dm.npd = hm.npd; dm.ng = d == 3 ? 6 : 3;
+  dm.E = hm.E; dm.N1 = (size_t)hm.E * hm.np1; dm.N2 = (size_t)hm.E * hm.np2; dm.Nd = (size_t)hm.E * hm.npd;
+  dm.has_outflow = hm.has_outflow; dm.nvert = hm.nvert;
+  const size_t N1 = dm.N1, N2 = dm.N2;
+  // 1-D operators
+  if (dev_upload(c, &dm.D, b.D) || dev_upload(c, &dm.Dt, mat_transpose(b.D, n, n)) || dev_upload(c, &dm.I12, b.I12) ||
+      dev_upload(c, &dm.I12t, mat_transpose(b.I12, q, n)) || dev_upload(c, &dm.D12, b.D12) || dev_upload(c, &dm.D12t, mat_transpose(b.D12, q, n)) ||
+      dev_upload(c, &dm.I1d, b.I1d) || dev_upload(c, &dm.I1dt, mat_transpose(b.I1d, m, n)) || dev_upload(c, &dm.Dd, b.Dd) ||
+      dev_upload(c, &dm.Ddt, mat_transpose(b.Dd, m, m))) return 1;
+  { std::vector<double> wz(b.w2); wz.insert(wz.end(), b.z2.begin(), b.z2.end()); if (dev_upload(c, &dm.w2, wz)) return 1; }
+  // geometry (packed [E][k][np])
+  {
+    std::vector<double> G((size_t)hm.E * dm.ng * hm.np1);
+    const int order3[6] = {0, 1, 2, 3, 4, 5}, order2[3] = {0, 1, 3};
+    for (int64_t e = 0; e < hm.E; ++e) for (int k = 0; k < dm.ng; ++k) {
+      const std::vector<double>& src = hm.G[d == 3 ? order3[k] : order2[k]];
+      std::copy(src.begin() + e * hm.np1, src.begin() + (e + 1) * hm.np1, G.begin() + ((size_t)e * dm.ng + k) * hm.np1);
+    }
+    if (dev_upload(c, &dm.G, G)) return 1;
+    std::vector<double> R((size_t)hm.E * d * d * hm.np2), Rd((size_t)hm.E * d * d * hm.npd), Rj((size_t)hm.E * d * d * hm.np1);
+    for (int64_t e = 0; e < hm.E; ++e) for (int k = 0; k < d * d; ++k) {
+      std::copy(hm.rxw2[k].begin() + e * hm.np2, hm.rxw2[k].begin() + (e + 1) * hm.np2, R.begin() + ((size_t)e * d * d + k) * hm.np2);
+      std::copy(hm.rxd[k].begin() + e * hm.npd, hm.rxd[k].begin() + (e + 1) * hm.npd, Rd.begin() + ((size_t)e * d * d + k) * hm.npd);
+      for (int p = 0; p < hm.np1; ++p) Rj[((size_t)e * d * d + k) * hm.np1 + p] = hm.rx[k][e * hm.np1 + p] / hm.jac[e * hm.np1 + p];
+    }
+    if (dev_upload(c, &dm.rxw2, R) || dev_upload(c, &dm.rxd, Rd) || dev_upload(c, &dm.rxj, Rj)) return 1;
+  }
+  if (dev_upload(c, &dm.bm1, hm.bm1) || dev_upload(c, &dm.bm2, hm.bm2)) return 1;
+  for (int k = 0; k < d; ++k) if (dev_upload(c, &dm.mask[k], hm.vmask[k])) return 1;
+  if (dev_upload(c, &dm.mask[3], hm.tmask)) return 1;
+  {
+    std::vector<double> ml(N2), mu(N2), bi(N2), ones(N2, 1.0);
+    for (size_t i = 0; i < N2; ++i) { ml[i] = std::sqrt(1.0 / hm.bm2[i]); mu[i] = std::sqrt(hm.bm2[i]); bi[i] = 1.0 / hm.bm2[i]; }
+    if (dev_upload(c, &dm.ml, ml) || dev_upload(c, &dm.mu, mu) || dev_upload(c, &c->pw[5], bi) || dev_upload(c, &c->ones2, ones)) return 1;
+    std::vector<double> dri(n);
+    dri[0] = 1.0 / (b.z1[1] - b.z1[0]); dri[n - 1] = 1.0 / (b.z1[n - 1] - b.z1[n - 2]);
+    for (int i = 1; i < n - 1; ++i) dri[i] = 2.0 / (b.z1[i + 1] - b.z1[i - 1]);
+    if (dev_upload(c, &dm.dri, dri)) return 1;
+  }
+  if (dev_upload(c, &dm.gs_off, hm.gs_off) || dev_upload(c, &dm.gs_idx, hm.gs_idx)) return 1;
+  dm.ngs = (int)hm.gs_off.size() - 1;
+  if (dev_upload(c, &dm.vertex, hm.vertex_local) || dev_upload(c, &dm.vert_off, hm.vert_off) || dev_upload(c, &dm.vert_ec, hm.vert_ec)) return 1;
+  for (int k = 0; k < d; ++k) if (dev_upload(c, &c->xyz[k], hm.xyz[k])) return 1;
+  if (dev_upload(c, &c->d_lglel, hm.lglel)) return 1;
+  // neighbours (multi-rank)
+  for (const Neighbor& nb : hm.neigh) {
+    DevNeighbor dn{}; dn.rank = nb.rank; dn.cnt = (int)nb.gids.size();
+    // local copies of each shared node: look the gid up in the interface CSR
+    std::vector<int32_t> off(1, 0), idx;
+    for (size_t i = 0; i < nb.gids.size(); ++i) {
+      auto it = std::lower_bound(hm.if_gids.begin(), hm.if_gids.end(), nb.gids[i]);
+      size_t g = it - hm.if_gids.begin();
+      for (int32_t u = hm.if_off[g]; u < hm.if_off[g + 1]; ++u) idx.push_back(hm.if_idx[u]);
+      off.push_back((int32_t)idx.size());
+    }
+    if (dev_upload(c, &dn.rep, nb.rep) || dev_upload(c, &dn.cp_off, off) || dev_upload(c, &dn.cp_idx, idx)) return 1;
+    if (dev_alloc(c, &dn.sendbuf, (size_t)3 * dn.cnt) || dev_alloc(c, &dn.recvbuf, (size_t)3 * dn.cnt)) return 1;
+    c->neigh.push_back(dn);
+  }
+  // scalars / reducer
+  if (dev_alloc(c, &c->d_sc, 1) || dev_alloc(c, &c->d_red, 512)) return 1;
+  NLK_CUDA(cudaMallocHost((void**)&c->h_sc, sizeof(SolverScal)));
+  NLK_CUDA(cudaMallocHost((void**)&c->h_red, sizeof(double) * 512));
+  c->red.maxblocks = 1024;
+  if (dev_alloc(c, &c->red.partial, (size_t)16 * c->red.maxblocks) || dev_alloc(c, &c->red.counter, 1)) return 1;
+  // state + work arrays
+  for (int k = 0; k < 3; ++k) {
+    if (k < d) {
+      if (dev_alloc(c, &c->U[k], N1) || dev_alloc(c, &c->vp[k], N1) || dev_alloc(c, &c->vlag[0][k], N1) || dev_alloc(c, &c->vlag[1][k], N1) ||
+          dev_alloc(c, &c->exx1[k], N1) || dev_alloc(c, &c->exx2[k], N1) || dev_alloc(c, &c->bf[k], N1)) return 1;
+    }
+  }
+  if (dev_alloc(c, &c->T, N1) || dev_alloc(c, &c->tp, N1) || dev_alloc(c, &c->prp, N2) || dev_alloc(c, &c->prlag, N2)) return 1;
+  if (c->prm.ifheat) { if (dev_alloc(c, &c->tlag[0], N1) || dev_alloc(c, &c->tlag[1], N1) || dev_alloc(c, &c->vgradt1, N1) || dev_alloc(c, &c->vgradt2, N1) || dev_alloc(c, &c->bq, N1)) return 1; }
+  for (int k = 0; k < 8; ++k) if (dev_alloc(c, &c->wk[k], N1)) return 1;
+  if (dev_alloc(c, &c->cg_x, N1) || dev_alloc(c, &c->cg_r, N1) || dev_alloc(c, &c->cg_p, N1) || dev_alloc(c, &c->cg_w, N1)) return 1;
+  for (int k = 0; k < 5; ++k) if (dev_alloc(c, &c->pw[k], N2)) return 1;
+  if (dev_alloc(c, &c->gm_V, (size_t)(c->prm.lgmres + 1) * N2) || dev_alloc(c, &c->gm_Z, (size_t)c->prm.lgmres * N2)) return 1;
+  if (dev_alloc(c, &c->sw_w, N1) || dev_alloc(c, &c->sw_z, N1) || dev_alloc(c, &c->sw_t, N1)) return 1;
+  // ---- device-side setup: global volumes, binvm1, vmult, Jacobi diagonals
+  {
+    double vols[3] = {hm.volvm1, hm.volvm2, (double)N2};
+    NLK_CUDA(cudaMemcpyAsync(c->d_red, vols, sizeof(vols), cudaMemcpyHostToDevice, c->st));
+    if (ctx_allreduce(c, c->d_red, 3, false)) return 1;
+    if (ctx_read_scalars(c, 3)) return 1;
+    dm.volvm1 = c->h_red[0]; dm.volvm2 = c->h_red[1]; dm.N2_global = (int64_t)std::llround(c->h_red[2]);
+  }
+  if (dev_alloc(c, &dm.binvm1, N1) || dev_alloc(c, &dm.vmult, N1) || dev_alloc(c, &dm.diagA, N1) || dev_alloc(c, &dm.diagB, N1)) return 1;
+  NLK_CUDA(cudaMemcpyAsync(dm.diagB, dm.bm1, N1 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+  launch_fill(dm.vmult, N1, 1.0, c->st);
+  {
+    std::vector<double> dA(N1);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < hm.E; ++e) for (int p = 0; p < hm.np1; ++p) dA[(size_t)e * hm.np1 + p] = mesh_diag_local(hm, e, p);
+    NLK_CUDA(cudaMemcpyAsync(dm.diagA, dA.data(), N1 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    NLK_CUDA(cudaStreamSynchronize(c->st));
+  }
+  if (ctx_gs(c, Ptr3{{dm.diagB, dm.vmult, dm.diagA}}, 3)) return 1;
+  launch_recip(dm.binvm1, dm.diagB, N1, c->st);
+  launch_recip(dm.vmult, dm.vmult, N1, c->st);
+  // filter
+  if (c->prm.filter_weight > 0) { std::vector<double> F; make_filter_matrix(b, c->prm.filter_weight, c->prm.filter_cutoff, F); if (dev_upload(c, &c->filterF, F)) return 1; }
+  // ---- Schwarz + coarse preconditioner
+  if (c->prm.precond >= 1) {
+    const int np1 = hm.np1;
+    // element lengths per direction; neighbour lengths through a face dssum
+    std::vector<double> len((size_t)hm.E * d), wl(N1 * (size_t)d, 0.0);
+    for (int64_t e = 0; e < hm.E; ++e) for (int k = 0; k < d; ++k) {
+      double s = 0; int cnt = 0;
+      int nz = d == 3 ? n : 1;
+      for (int a2 = 0; a2 < nz; ++a2) for (int a1 = 0; a1 < n; ++a1) {
+        // (a1,a2) enumerate the face nodes; compute lo/hi point indices along direction k
+        int idx_lo[3], idx_hi[3]; int t = 0;
+        for (int dd = 0; dd < 3; ++dd) { if (dd == k) { idx_lo[dd] = 0; idx_hi[dd] = n - 1; } else { int v = (t == 0 ? a1 : a2); idx_lo[dd] = idx_hi[dd] = v; ++t; } }
+        if (d == 2) { idx_lo[2] = idx_hi[2] = 0; if (a2 > 0) continue; }
+        int plo = (idx_lo[2] * n + idx_lo[1]) * n + idx_lo[0], phi = (idx_hi[2] * n + idx_hi[1]) * n + idx_hi[0];
+        double dist = 0;
+        for (int cc = 0; cc < d; ++cc) { double dx = hm.xyz[cc][e * np1 + phi] - hm.xyz[cc][e * np1 + plo]; dist += dx * dx; }
+        s += std::sqrt(dist); ++cnt;
+      }
+      len[e * d + k] = s / cnt;
+      // write the length on both faces normal to k (all face nodes)
+      for (int p = 0; p < np1; ++p) {
+        int ijk[3] = {p % n, (p / n) % n, d == 3 ? p / (n * n) : 0};
+        if (ijk[k] == 0 || ijk[k] == n - 1) wl[(size_t)k * N1 + e * np1 + p] = len[e * d + k];
+      }
+    }
+    double* dwl = nullptr;
+    if (dev_upload(c, &dwl, wl)) return 1;
+    if (ctx_gs(c, Ptr3{{dwl, dwl + N1, d == 3 ? dwl + 2 * N1 : nullptr}}, d)) return 1;
+    NLK_CUDA(cudaMemcpyAsync(wl.data(), dwl, wl.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    NLK_CUDA(cudaStreamSynchronize(c->st));
+    std::vector<double> S((size_t)hm.E * d * n * n), St((size_t)hm.E * d * n * n), dinv(N1, 0.0);
+    const int mid = n / 2;
+    static const int F_LO[3] = {3, 0, 4}, F_HI[3] = {1, 2, 5};
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < hm.E; ++e) {
+      std::vector<double> lam((size_t)d * n); int nact[3] = {1, 1, 1};
+      for (int k = 0; k < d; ++k) {
+        int ijk_lo[3] = {mid, mid, d == 3 ? mid : 0}, ijk_hi[3] = {mid, mid, d == 3 ? mid : 0};
+        ijk_lo[k] = 0; ijk_hi[k] = n - 1;
+        double lm = len[e * d + k];
+        double ll = wl[(size_t)k * N1 + e * np1 + (ijk_lo[2] * n + ijk_lo[1]) * n + ijk_lo[0]] - lm;
+        double lr = wl[(size_t)k * N1 + e * np1 + (ijk_hi[2] * n + ijk_hi[1]) * n + ijk_hi[0]] - lm;
+        if (std::fabs(ll) < 1e-12 * lm) ll = 0; if (std::fabs(lr) < 1e-12 * lm) lr = 0;
+        auto bc_of = [&](double lnb, int f) { if (lnb > 0) return 0; const auto& cb = hm.cbc_v[e * hm.nfaces + f]; return (cb[0] == 'O' || cb[0] == 'o') ? 1 : 2; };
+        int bcl = bc_of(ll, F_LO[k]), bcr = bc_of(lr, F_HI[k]);
+        make_fdm_1d(b, lm, ll, lr, bcl, bcr, &S[((size_t)e * d + k) * n * n], &lam[(size_t)k * n], &nact[k]);
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) St[((size_t)e * d + k) * n * n + j * n + i] = S[((size_t)e * d + k) * n * n + i * n + j];
+      }
+      double maxden = 0;
+      for (int p = 0; p < np1; ++p) {
+        int i = p % n, j = (p / n) % n, k = d == 3 ? p / (n * n) : 0;
+        bool act = i < nact[0] && j < nact[1] && (d == 2 || k < nact[2]);
+        if (act) { double den = lam[i] + lam[n + j] + (d == 3 ? lam[2 * n + k] : 0.0); maxden = std::max(maxden, std::fabs(den)); }
+      }
+      for (int p = 0; p < np1; ++p) {
+        int i = p % n, j = (p / n) % n, k = d == 3 ? p / (n * n) : 0;
+        bool act = i < nact[0] && j < nact[1] && (d == 2 || k < nact[2]);
+        double den = lam[i] + lam[n + j] + (d == 3 ? lam[2 * n + k] : 0.0);
+        dinv[(size_t)e * np1 + p] = (act && den > 1e-12 * maxden) ? 1.0 / den : 0.0;
+      }
+    }
+    if (dev_upload(c, &dm.fdmS, S) || dev_upload(c, &dm.fdmSt, St) || dev_upload(c, &dm.fdmDinv, dinv)) return 1;
+    // overlap-count weights
+    if (dev_alloc(c, &dm.swt, N2)) return 1;
+    launch_schwarz_embed(dm, c->ones2, c->sw_w, c->st);
+    if (ctx_gs(c, Ptr3{{c->sw_w, nullptr, nullptr}}, 1)) return 1;
+    launch_schwarz_count(dm, c->sw_w, c->sw_z, c->sw_t, c->st);
+    if (ctx_gs(c, Ptr3{{c->sw_t, nullptr, nullptr}}, 1)) return 1;
+    launch_schwarz_gather_nowt(dm, c->sw_z, c->sw_t, dm.swt, c->st);
+    launch_recip(dm.swt, dm.swt, N2, c->st);
+    c->have_schwarz = true;
+    // coarse operator A0 = R0 E R0^T, column by column on the device; dense inverse on the host
+    const int64_t nvt = hm.nvert;
+    if (nvt <= 12000 && c->prm.precond != 2) {
+      if (dev_alloc(c, &c->crs_part, (size_t)hm.E << d) || dev_alloc(c, &c->crs_r, nvt) || dev_alloc(c, &c->crs_y, nvt)) return 1;
+      double* dA0 = nullptr; if (dev_alloc(c, &dA0, (size_t)nvt * nvt)) return 1;
+      for (int64_t v = 0; v < nvt; ++v) {
+        NLK_CUDA(cudaMemsetAsync(c->crs_y, 0, nvt * sizeof(double), c->st));
+        launch_fill(c->crs_y + v, 1, 1.0, c->st);
+        launch_coarse_prolong_add(dm, c->crs_y, c->pw[0], 0, c->st);
+        if (apply_E(c, c->pw[0], c->pw[1])) return 1;
+        launch_coarse_restrict(dm, c->pw[1], c->crs_part, dA0 + (size_t)v * nvt, c->st);
+      }
+      if (ctx_allreduce(c, dA0, (int)(nvt * nvt), false)) return 1;
+      std::vector<double> A0((size_t)nvt * nvt);
+      NLK_CUDA(cudaMemcpyAsync(A0.data(), dA0, A0.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+      NLK_CUDA(cudaStreamSynchronize(c->st));
+      for (int64_t i = 0; i < nvt; ++i) for (int64_t j = 0; j < i; ++j) { double s = 0.5 * (A0[i * nvt + j] + A0[j * nvt + i]); A0[i * nvt + j] = A0[j * nvt + i] = s; }
+      if (!hm.has_outflow) {   // singular (constant null space): shift along 1 1^T -- the solution changes by a constant, removed by ortho
+        double tr = 0; for (int64_t i = 0; i < nvt; ++i) tr += A0[i * nvt + i];
+        const double sft = tr / ((double)nvt * (double)nvt);
+        for (size_t i = 0; i < A0.size(); ++i) A0[i] += sft;
+      }
+      if (spd_inverse((int)nvt, A0.data(), false)) return 1;
+      dm.A0inv = dA0;
+      NLK_CUDA(cudaMemcpyAsync(dA0, A0.data(), A0.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
+      NLK_CUDA(cudaStreamSynchronize(c->st));
+      c->have_coarse = true;
+    }
+  }
+  NLK_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+}  // namespace nlk
+
+extern "C" {
+
+int nlk_params_default(nlk_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->viscosity = 1.0; p->density = 1.0; p->torder = 3; p->vtol = 1e-9; p->ptol = 1e-7; p->ifheat = 0; p->conductivity = 1.0; p->rhocp = 1.0;
+  p->ttol = 1e-9; p->filter_weight = 0.0; p->filter_cutoff = 1.0; p->cg_maxit = 1000; p->gmres_maxit = 100; p->lgmres = 30; p->precond = 1;
+  p->pr_proj = 0; p->cfl_limit = 0.5;
+  return 0;
+}
+
+int nlk_comm_unique_id(char id[128]) {
+  Nccl n; if (nccl_load(n)) return 1;
+  NcclId u; int r = n.GetUniqueId(&u); if (r) { set_error("ncclGetUniqueId failed"); return 1; }
+  std::memcpy(id, u.internal, 128); return 0;
+}
+
+int nlk_ctx_create(const nlk_mesh* m, const nlk_params* p, int32_t device, nlk_ctx** out) {
+  if (!m || !p || !out) { set_error("null argument"); return 1; }
+  if (check_device()) return 1;
+  if (p->torder < 1 || p->torder > 3) { set_error("torder must be 1..3"); return 1; }
+  if (p->lgmres < 1 || p->lgmres > 200) { set_error("lgmres out of range"); return 1; }
+  NLK_CUDA(cudaSetDevice(device));
+  nlk_ctx* c = new nlk_ctx(); c->mesh = m; c->prm = *p; c->device = device;
+  NLK_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  *out = c;
+  if (m->hm.nranks > 1) return 0;            // multi-rank: setup is finished by nlk_ctx_comm_init
+  if (ctx_setup(c)) return 1;
+  return 0;
+}
+
+int nlk_ctx_comm_init(nlk_ctx* c, const char id[128], int32_t rank, int32_t nranks) {
+  if (nranks != c->mesh->hm.nranks || rank != c->mesh->hm.rank) { set_error("rank/nranks do not match the mesh partition"); return 1; }
+  if (nranks > 1) {
+    if (nccl_load(c->nccl)) return 1;
+    NcclId u; std::memcpy(u.internal, id, 128);
+    int r = c->nccl.CommInitRank(&c->nccl.comm, nranks, u, rank);
+    if (r) { set_error(std::string("ncclCommInitRank failed: ") + c->nccl.GetErrorString(r)); return 1; }
+    c->nccl.rank = rank; c->nccl.nranks = nranks;
+  }
+  return ctx_setup(c);
+}
+
+int nlk_ctx_destroy(nlk_ctx* c) {
+  if (!c) return 0;
+  cudaStreamSynchronize(c->st);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->h_sc) cudaFreeHost(c->h_sc);
+  if (c->h_red) cudaFreeHost(c->h_red);
+  if (c->nccl.comm) c->nccl.CommDestroy(c->nccl.comm);
+  cudaStreamDestroy(c->st);
+  delete c; return 0;
+}
+int nlk_ctx_set_tol(nlk_ctx* c, double vtol, double ptol) { c->prm.vtol = vtol; c->prm.ptol = ptol; return 0; }
+int nlk_ctx_sync(nlk_ctx* c) { NLK_CUDA(cudaStreamSynchronize(c->st)); return 0; }
+void* nlk_ctx_stream(nlk_ctx* c) { return (void*)c->st; }
+
+int nlk_ctx_set_forcing(nlk_ctx* c, const double* fx, const double* fy, const double* fz) {
+  const double* f[3] = {fx, fy, fz};
+  for (int k = 0; k < c->dm.ndim; ++k) {
+    if (!c->forcing[k]) { if (dev_alloc(c, &c->forcing[k], c->dm.N1)) return 1; }
+    if (f[k]) NLK_CUDA(cudaMemcpyAsync(c->forcing[k], f[k], c->dm.N1 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    else NLK_CUDA(cudaMemsetAsync(c->forcing[k], 0, c->dm.N1 * sizeof(double), c->st));
+  }
+  NLK_CUDA(cudaStreamSynchronize(c->st));
+  c->has_forcing = true; return 0;
+}
+
+// ============================================================================================== nek_dvector
+int nlk_vec_create(nlk_ctx* c, nlk_vec** out) {
+  nlk_vec* v = new nlk_vec(); v->c = c;
+  for (int k = 0; k < c->dm.ndim; ++k) if (dev_alloc(c, &v->v[k], c->dm.N1)) return 1;
+  if (dev_alloc(c, &v->pr, c->dm.N2) || dev_alloc(c, &v->theta, c->dm.N1)) return 1;
+  *out = v; return 0;
+}
+int nlk_vec_destroy(nlk_vec* v) {
+  if (!v) return 0;
+  nlk_ctx* c = v->c;
+  auto rel = [&](double* p) { if (!p) return; auto it = std::find(c->allocs.begin(), c->allocs.end(), (void*)p); if (it != c->allocs.end()) { cudaFree(p); c->allocs.erase(it); } };
+  cudaStreamSynchronize(c->st);
+  for (int k = 0; k < 3; ++k) { rel(v->v[k]); for (int s = 0; s < 2; ++s) rel(v->rv[s][k]); }
+  rel(v->pr); rel(v->theta);
+  for (int s = 0; s < 2; ++s) { rel(v->rpr[s]); rel(v->rth[s]); }
+  delete v; return 0;
+}
+}  // extern "C"
+
+namespace nlk {
+int vec_alloc_rst(nlk_vec* v, int s) {
+  nlk_ctx* c = v->c;
+  if (v->rpr[s]) return 0;
+  for (int k = 0; k < c->dm.ndim; ++k) if (dev_alloc(c, &v->rv[s][k], c->dm.N1)) return 1;
+  if (dev_alloc(c, &v->rpr[s], c->dm.N2) || dev_alloc(c, &v->rth[s], c->dm.N1)) return 1;
+  return 0;
+}
+static int copy_fields(nlk_ctx* c, double* const dv[3], double* dp, double* dt, const double* const sv[3], const double* sp, const double* stt) {
+  const DevMesh& dm = c->dm;
+  for (int k = 0; k < dm.ndim; ++k) NLK_CUDA(cudaMemcpyAsync(dv[k], sv[k], dm.N1 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+  NLK_CUDA(cudaMemcpyAsync(dp, sp, dm.N2 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+  if (c->prm.ifheat) NLK_CUDA(cudaMemcpyAsync(dt, stt, dm.N1 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+  return 0;
+}
+}  // namespace nlk
+
+extern "C" {
+
+int nlk_vec_copy(nlk_vec* dst, const nlk_vec* src) {
+  nlk_ctx* c = dst->c;
+  if (copy_fields(c, dst->v, dst->pr, dst->theta, src->v, src->pr, src->theta)) return 1;
+  dst->nrst = src->nrst;
+  for (int s = 0; s < src->nrst; ++s) {
+    if (vec_alloc_rst(dst, s)) return 1;
+    if (copy_fields(c, dst->rv[s], dst->rpr[s], dst->rth[s], src->rv[s], src->rpr[s], src->rth[s])) return 1;
+  }
+  return 0;
+}
+int nlk_vec_zero(nlk_vec* v) {
+  nlk_ctx* c = v->c; const DevMesh& dm = c->dm;
+  for (int k = 0; k < dm.ndim; ++k) NLK_CUDA(cudaMemsetAsync(v->v[k], 0, dm.N1 * sizeof(double), c->st));
+  NLK_CUDA(cudaMemsetAsync(v->pr, 0, dm.N2 * sizeof(double), c->st));
+  NLK_CUDA(cudaMemsetAsync(v->theta, 0, dm.N1 * sizeof(double), c->st));
+  v->nrst = 0; return 0;
+}
+int nlk_vec_scal(nlk_vec* v, double a) {
+  nlk_ctx* c = v->c; const DevMesh& dm = c->dm;
+  auto sc = [&](double* const f[3], double* p, double* t) {
+    for (int k = 0; k < dm.ndim; ++k) launch_lin(f[k], dm.N1, a, f[k], 0, nullptr, 0, nullptr, 0, nullptr, nullptr, c->st);
+    launch_lin(p, dm.N2, a, p, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, c->st);
+    if (c->prm.ifheat) launch_lin(t, dm.N1, a, t, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, c->st);
+  };
+  sc(v->v, v->pr, v->theta);
+  for (int s = 0; s < v->nrst; ++s) sc(v->rv[s], v->rpr[s], v->rth[s]);
+  return 0;
+}
+// self = alpha*x + beta*self ; rst slots of self get alpha * (x's CURRENT fields)  (real_vectors.f90:186-200)
+int nlk_vec_axpby(double alpha, const nlk_vec* x, double beta, nlk_vec* self) {
+  nlk_ctx* c = self->c; const DevMesh& dm = c->dm;
+  auto ax = [&](double* const f[3], double* p, double* t) {
+    for (int k = 0; k < dm.ndim; ++k) launch_lin(f[k], dm.N1, beta, f[k], alpha, x->v[k], 0, nullptr, 0, nullptr, nullptr, c->st);
+    launch_lin(p, dm.N2, beta, p, alpha, x->pr, 0, nullptr, 0, nullptr, nullptr, c->st);
+    if (c->prm.ifheat) launch_lin(t, dm.N1, beta, t, alpha, x->theta, 0, nullptr, 0, nullptr, nullptr, c->st);
+  };
+  ax(self->v, self->pr, self->theta);
+  for (int s = 0; s < self->nrst; ++s) ax(self->rv[s], self->rpr[s], self->rth[s]);
+  return 0;
+}
+int nlk_vec_dot(const nlk_vec* a, const nlk_vec* b, double* out) {
+  nlk_ctx* c = a->c; const DevMesh& dm = c->dm;
+  CPtr4 A{}, B{}; int np = 0;
+  for (int k = 0; k < dm.ndim; ++k) { A.p[np] = a->v[k]; B.p[np] = b->v[k]; ++np; }
+  if (c->prm.ifheat) { A.p[np] = a->theta; B.p[np] = b->theta; ++np; }
+  launch_dot(dm.N1, A, B, np, dm.bm1, c->d_red + 310, c->red, c->st);
+  if (ctx_allreduce(c, c->d_red + 310, 1, false)) return 1;
+  NLK_CUDA(cudaMemcpyAsync(c->h_red + 310, c->d_red + 310, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  NLK_CUDA(cudaStreamSynchronize(c->st));
+  *out = c->h_red[310]; return 0;
+}
+int nlk_vec_norm(const nlk_vec* a, double* out) { double d; if (nlk_vec_dot(a, a, &d)) return 1; *out = std::sqrt(d); return 0; }
+int nlk_vec_size(const nlk_vec* v, int64_t* n) {
+  const DevMesh& dm = v->c->dm;
+  *n = (int64_t)dm.ndim * dm.N1 + dm.N2 + (v->c->prm.ifheat ? dm.N1 : 0); return 0;
+}
+int nlk_vec_save_rst(nlk_vec* self, const nlk_vec* st, int32_t irst) {
+  nlk_ctx* c = self->c;
+  if (irst < 1 || irst >= c->prm.torder) { set_error("save_rst: cannot save rst field irst for this temporal order"); return 1; }
+  if (vec_alloc_rst(self, irst - 1)) return 1;
+  if (copy_fields(c, self->rv[irst - 1], self->rpr[irst - 1], self->rth[irst - 1], st->v, st->pr, st->theta)) return 1;
+  self->nrst = std::max(self->nrst, irst); return 0;
+}
+int nlk_vec_get_rst(const nlk_vec* self, nlk_vec* out, int32_t irst) {
+  nlk_ctx* c = self->c;
+  if (irst < 1 || irst > self->nrst) { set_error("get_rst: no rst field to retrieve"); return 1; }
+  if (copy_fields(c, out->v, out->pr, out->theta, self->rv[irst - 1], self->rpr[irst - 1], self->rth[irst - 1])) return 1;
+  out->nrst = 0; return 0;
+}
+int nlk_vec_nrst(const nlk_vec* v, int32_t* nrst) { *nrst = v->nrst; return 0; }
+int nlk_vec_clear_rst(nlk_vec* v) { v->nrst = 0; return 0; }
+
+int nlk_vec_upload(nlk_vec* v, const double* vx, const double* vy, const double* vz, const double* pr, const double* theta) {
+  nlk_ctx* c = v->c; const DevMesh& dm = c->dm;
+  const double* f[3] = {vx, vy, vz};
+  for (int k = 0; k < dm.ndim; ++k) if (f[k]) NLK_CUDA(cudaMemcpyAsync(v->v[k], f[k], dm.N1 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  if (pr) NLK_CUDA(cudaMemcpyAsync(v->pr, pr, dm.N2 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  if (theta) NLK_CUDA(cudaMemcpyAsync(v->theta, theta, dm.N1 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  NLK_CUDA(cudaStreamSynchronize(c->st));
+  v->nrst = 0; return 0;
+}
+int nlk_vec_download(const nlk_vec* v, double* vx, double* vy, double* vz, double* pr, double* theta) {
+  nlk_ctx* c = v->c; const DevMesh& dm = c->dm;
+  double* f[3] = {vx, vy, vz};
+  for (int k = 0; k < dm.ndim; ++k) if (f[k]) NLK_CUDA(cudaMemcpyAsync(f[k], v->v[k], dm.N1 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  if (pr) NLK_CUDA(cudaMemcpyAsync(pr, v->pr, dm.N2 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  if (theta) NLK_CUDA(cudaMemcpyAsync(theta, v->theta, dm.N1 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  NLK_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// seeded, C0, BC-satisfying random vector (nek_drand: real_vectors.f90:52-123 -- random_number is compiler-specific,
+// so the generator is a documented replacement: smooth field + splitmix64 noise, then dssum*vmult, mask, normalise)
+int nlk_vec_rand(nlk_vec* v, int32_t ifnorm, uint64_t seed) {
+  nlk_ctx* c = v->c; const DevMesh& dm = c->dm;
+  if (nlk_vec_zero(v)) return 1;
+  for (int k = 0; k < dm.ndim; ++k) launch_rand_field_impl(v->v[k], c->xyz[0], c->xyz[1], dm.ndim == 3 ? c->xyz[2] : nullptr, c->d_lglel, dm.np1, dm.N1, seed, k, c->st);
+  if (ctx_gs(c, Ptr3{{v->v[0], v->v[1], v->v[2]}}, dm.ndim)) return 1;
+  for (int k = 0; k < dm.ndim; ++k) launch_axpy_mm(v->v[k], dm.N1, nullptr, 1.0, v->v[k], dm.vmult, dm.mask[k], c->st);
+  if (c->prm.ifheat) {
+    launch_rand_field_impl(v->theta, c->xyz[0], c->xyz[1], dm.ndim == 3 ? c->xyz[2] : nullptr, c->d_lglel, dm.np1, dm.N1, seed, 7, c->st);
+    if (ctx_gs(c, Ptr3{{v->theta, nullptr, nullptr}}, 1)) return 1;
+    launch_axpy_mm(v->theta, dm.N1, nullptr, 1.0, v->theta, dm.vmult, dm.mask[3], c->st);
+  }
+  if (ifnorm) { double nr; if (nlk_vec_norm(v, &nr)) return 1; if (nlk_vec_scal(v, 1.0 / nr)) return 1; }
+  v->nrst = 0; return 0;
+}
+
+// ============================================================================================== exptA
+int nlk_exptA_create(nlk_ctx* c, double tau, const nlk_vec* bf, nlk_op** out) {
+  nlk_op* op = new nlk_op(); op->c = c; op->tau = tau;
+  if (nlk_vec_create(c, &op->baseflow)) return 1;
+  if (nlk_vec_copy(op->baseflow, bf)) return 1;
+  *out = op; return 0;
+}
+int nlk_exptA_destroy(nlk_op* op) { if (!op) return 0; nlk_vec_destroy(op->baseflow); delete op; return 0; }
+int nlk_exptA_set_tau(nlk_op* op, double tau) { op->tau = tau; return 0; }
+}  // extern "C"
+
+namespace nlk {
+static int push_baseflow(nlk_op* op) {            // vec2nek(vx,vy,vz,pr,t, self%baseflow)
+  nlk_ctx* c = op->c; const DevMesh& dm = c->dm;
+  for (int k = 0; k < dm.ndim; ++k) NLK_CUDA(cudaMemcpyAsync(c->U[k], op->baseflow->v[k], dm.N1 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+  NLK_CUDA(cudaMemcpyAsync(c->T, op->baseflow->theta, dm.N1 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+  return 0;
+}
+static int state_from_vec(nlk_ctx* c, const double* const v[3], const double* pr, const double* th) {
+  return copy_fields(c, c->vp, c->prp, c->tp, v, pr, th);
+}
+
+// exptA_matvec / exptA_rmatvec (src/linops/exponential_propagator.f90:15-107) incl. get_rst / compute_rst (:109-142)
+int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose) {
+  nlk_ctx* c = op->c;
+  if (in == out) { set_error("exptA: vec_in and vec_out must differ"); return 1; }
+  const int nrst = c->prm.torder - 1;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  long l0 = g_launches; long cg0 = c->cg_iters, gm0 = c->gmres_iters, st0 = c->steps;
+  cudaEventRecord(e0, c->st);
+  if (push_baseflow(op)) return 1;
+  if (step_setup(c, op->tau, transpose)) return 1;
+  if (state_from_vec(c, in->v, in->pr, in->theta)) return 1;
+  if (reset_history_pub(c)) return 1;
+  for (int istep = 1; istep <= c->nsteps; ++istep) {
+    if (step_advance(c, istep)) return 1;
+    if (istep <= nrst && in->nrst > 0) {
+      if (istep > in->nrst) { set_error("exptA: input vector has fewer rst fields than the temporal order needs"); return 1; }
+      if (state_from_vec(c, in->rv[istep - 1], in->rpr[istep - 1], in->rth[istep - 1])) return 1;
+    }
+  }
+  if (copy_fields(c, out->v, out->pr, out->theta, c->vp, c->prp, c->tp)) return 1;       // nek2vec (intent(out): nrst reset)
+  out->nrst = 0;
+  for (int k = 1; k <= nrst; ++k) {
+    if (step_advance(c, c->nsteps + k)) return 1;
+    if (vec_alloc_rst(out, k - 1)) return 1;
+    if (copy_fields(c, out->rv[k - 1], out->rpr[k - 1], out->rth[k - 1], c->vp, c->prp, c->tp)) return 1;
+    out->nrst = std::max(out->nrst, k);
+  }
+  cudaEventRecord(e1, c->st);
+  NLK_CUDA(cudaStreamSynchronize(c->st));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  op->stats.nsteps = c->nsteps; op->stats.dt = c->dt; op->stats.ms_total = ms; op->stats.launches = g_launches - l0;
+  op->stats.cg_iters = c->cg_iters - cg0; op->stats.gmres_iters = c->gmres_iters - gm0; op->stats.steps = c->steps - st0; op->stats.matvecs += 1;
+  return 0;
+}
+}  // namespace nlk
+
+extern "C" {
+int nlk_exptA_init(nlk_op* op) { if (push_baseflow(op)) return 1; return step_setup(op->c, op->tau, false); }
+int nlk_exptA_matvec(nlk_op* op, const nlk_vec* in, nlk_vec* out) { return exptA_apply(op, in, out, false); }
+int nlk_exptA_rmatvec(nlk_op* op, const nlk_vec* in, nlk_vec* out) { return exptA_apply(op, in, out, true); }
+int nlk_exptA_stats(const nlk_op* op, nlk_stats* out) { *out = op->stats; out->nsteps = op->c->nsteps; out->dt = op->c->dt; return 0; }
+
+// ============================================================================================== test hooks
+static int up(nlk_ctx* c, double* d, const double* h, size_t n) { NLK_CUDA(cudaMemcpyAsync(d, h, n * sizeof(double), cudaMemcpyHostToDevice, c->st)); return 0; }
+static int down(nlk_ctx* c, double* h, const double* d, size_t n) { NLK_CUDA(cudaMemcpyAsync(h, d, n * sizeof(double), cudaMemcpyDeviceToHost, c->st)); NLK_CUDA(cudaStreamSynchronize(c->st)); return 0; }
+
+int nlk_test_axhelm(nlk_ctx* c, const double* u, double h1, double h2, double* w) {
+  if (up(c, c->wk[0], u, c->dm.N1)) return 1;
+  launch_axhelm(c->dm, c->wk[0], c->wk[1], h1, h2, c->st);
+  return down(c, w, c->wk[1], c->dm.N1);
+}
+int nlk_test_dssum(nlk_ctx* c, double* u) {
+  if (up(c, c->wk[0], u, c->dm.N1)) return 1;
+  if (ctx_gs(c, Ptr3{{c->wk[0], nullptr, nullptr}}, 1)) return 1;
+  return down(c, u, c->wk[0], c->dm.N1);
+}
+int nlk_test_opdiv(nlk_ctx* c, const double* ux, const double* uy, const double* uz, double* p) {
+  const double* u[3] = {ux, uy, uz};
+  for (int k = 0; k < c->dm.ndim; ++k) if (up(c, c->wk[k], u[k], c->dm.N1)) return 1;
+  launch_opdiv(c->dm, CPtr3{{c->wk[0], c->wk[1], c->wk[2]}}, c->pw[0], 1.0, c->st);
+  return down(c, p, c->pw[0], c->dm.N2);
+}
+int nlk_test_opgradt(nlk_ctx* c, const double* p, double* wx, double* wy, double* wz) {
+  if (up(c, c->pw[0], p, c->dm.N2)) return 1;
+  launch_opgradt(c->dm, c->pw[0], Ptr3{{c->wk[0], c->wk[1], c->wk[2]}}, c->st);
+  double* w[3] = {wx, wy, wz};
+  for (int k = 0; k < c->dm.ndim; ++k) if (down(c, w[k], c->wk[k], c->dm.N1)) return 1;
+  return 0;
+}
+int nlk_test_cdabdtp(nlk_ctx* c, const double* p, double* ep) {
+  if (up(c, c->pw[3], p, c->dm.N2)) return 1;
+  if (apply_E(c, c->pw[3], c->pw[4])) return 1;
+  return down(c, ep, c->pw[4], c->dm.N2);
+}
+int nlk_test_convect(nlk_ctx* c, const double* u, const double* cx, const double* cy, const double* cz, double* out) {
+  const double* cc[3] = {cx, cy, cz};
+  if (up(c, c->wk[3], u, c->dm.N1)) return 1;
+  for (int k = 0; k < c->dm.ndim; ++k) if (up(c, c->wk[k], cc[k], c->dm.N1)) return 1;
+  launch_convect(c->dm, CPtr4{{c->wk[3], nullptr, nullptr, nullptr}}, 1, CPtr3{{c->wk[0], c->wk[1], c->wk[2]}}, Ptr4{{c->wk[4], nullptr, nullptr, nullptr}}, 1.0, 0, c->st);
+  return down(c, out, c->wk[4], c->dm.N1);
+}
+int nlk_test_convect_adj(nlk_ctx* c, const double* const* U, const double* const* cf, double* const* out) {
+  const int d = c->dm.ndim;
+  for (int k = 0; k < d; ++k) { if (up(c, c->wk[k], U[k], c->dm.N1)) return 1; if (up(c, c->wk[3 + k], cf[k], c->dm.N1)) return 1; }
+  launch_convect_adj(c->dm, CPtr3{{c->wk[0], c->wk[1], c->wk[2]}}, CPtr3{{c->wk[3], c->wk[4], c->wk[5]}}, Ptr3{{c->cg_x, c->cg_r, c->cg_p}}, 1.0, 0, c->st);
+  double* o[3] = {c->cg_x, c->cg_r, c->cg_p};
+  for (int k = 0; k < d; ++k) if (down(c, out[k], o[k], c->dm.N1)) return 1;
+  return 0;
+}
+int nlk_test_helmholtz(nlk_ctx* c, const double* f, double h1, double h2, int32_t comp, double tol, double* x, int32_t* iters) {
+  if (up(c, c->wk[7], f, c->dm.N1)) return 1;
+  int it = 0;
+  if (helmholtz_solve(c, c->wk[7], h1, h2, c->dm.mask[comp], tol, c->cg_x, &it)) return 1;
+  if (iters) *iters = it;
+  return down(c, x, c->cg_x, c->dm.N1);
+}
+int nlk_test_pressure(nlk_ctx* c, const double* rhs, double tol, double* x, int32_t* iters) {
+  if (up(c, c->pw[4], rhs, c->dm.N2)) return 1;
+  int it = 0;
+  if (pressure_solve(c, c->pw[4], tol, c->pw[3], &it)) return 1;
+  if (iters) *iters = it;
+  return down(c, x, c->pw[3], c->dm.N2);
+}
+int nlk_test_precond(nlk_ctx* c, const double* r, double* z) {
+  if (up(c, c->pw[3], r, c->dm.N2)) return 1;
+  if (apply_precond(c, c->pw[3], c->pw[4])) return 1;
+  return down(c, z, c->pw[4], c->dm.N2);
+}
+int nlk_test_cfl(nlk_ctx* c, const double* ux, const double* uy, const double* uz, double dt, double* cfl) {
+  const double* u[3] = {ux, uy, uz};
+  for (int k = 0; k < c->dm.ndim; ++k) if (up(c, c->wk[k], u[k], c->dm.N1)) return 1;
+  launch_cfl(c->dm, CPtr3{{c->wk[0], c->wk[1], c->wk[2]}}, c->d_red, c->red, c->st);
+  if (ctx_allreduce(c, c->d_red, 1, true)) return 1;
+  if (ctx_read_scalars(c, 1)) return 1;
+  *cfl = dt * c->h_red[0]; return 0;
+}
+
+int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_launch, double* algo_bytes) {
+  const DevMesh& dm = c->dm; const int d = dm.ndim;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto run = [&]() -> int {
+    switch (which) {
+      case 0: launch_axhelm(dm, c->wk[0], c->wk[1], 1.0, 1.0, c->st); break;
+      case 1: return ctx_gs(c, Ptr3{{c->wk[0], nullptr, nullptr}}, 1);
+      case 2: return apply_E(c, c->pw[3], c->pw[4]);
+      case 3: launch_convect(dm, CPtr4{{c->wk[3], c->wk[4], c->wk[5], nullptr}}, d, CPtr3{{c->wk[0], c->wk[1], c->wk[2]}}, Ptr4{{c->bf[0], c->bf[1], c->bf[2], nullptr}}, 1.0, 0, c->st); break;
+      case 4: return apply_precond(c, c->pw[3], c->pw[4]);
+      case 5: { CPtr4 A{{c->wk[0], c->wk[1], c->wk[2], nullptr}}; launch_dot(dm.N1, A, A, d, dm.bm1, c->d_red, c->red, c->st); break; }
+      default: set_error("unknown bench kernel"); return 1;
+    }
+    return 0;
+  };
+  for (int i = 0; i < 3; ++i) if (run()) return 1;
+  cudaEventRecord(e0, c->st);
+  for (int i = 0; i < nrep; ++i) if (run()) return 1;
+  cudaEventRecord(e1, c->st);
+  NLK_CUDA(cudaStreamSynchronize(c->st));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_launch = ms / nrep;
+  double N1 = (double)dm.N1, N2 = (double)dm.N2;
+  double bytes = 0;
+  switch (which) {
+    case 0: bytes = (2 + dm.ng + 1) * 8.0 * N1; break;                      // u, w, g-factors, bm1
+    case 1: bytes = 16.0 * N1 * 0 + (double)c->mesh->hm.gs_idx.size() * (16.0 + 4.0); break;
+    case 2: bytes = 2 * 8.0 * N2 + 2.0 * d * d * 8.0 * N2 + d * (4 * 8.0) * N1; break;
+    case 3: bytes = (3.0 * d + d * d) * 8.0 * N1; break;
+    case 4: bytes = 2 * 8.0 * N2 + 6 * 8.0 * N1; break;
+    case 5: bytes = (d + 1) * 8.0 * N1; break;
+  }
+  if (algo_bytes) *algo_bytes = bytes;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// Solver context: device-resident equivalent of Nek5000's COMMON-block state for one perturbation (lpert = 1),
+// plus NCCL plumbing.  See SURVEY.md §8b "Global state".
+#pragma once
+#include "nlk_device.cuh"
+#include "../../include/nlk.h"
+
+struct nlk_mesh { nlk::HostMesh hm; };
+
+namespace nlk {
+
+// ---- NCCL through dlopen (libnccl.so.2: the copy torch already loaded, else the system one)
+struct NcclId { char internal[128]; };
+struct Nccl {
+  void* lib = nullptr;
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId /*ncclUniqueId by value*/, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+int nccl_load(Nccl& n);
+
+struct DevNeighbor {
+  int rank; int cnt;
+  int32_t* rep;          // [cnt] representative local index
+  int32_t* cp_off;       // [cnt+1]
+  int32_t* cp_idx;       // local copies of every shared node
+  double* sendbuf;       // [3*cnt]
+  double* recvbuf;
+};
+
+}  // namespace nlk
+
+struct nlk_ctx {
+  const nlk_mesh* mesh = nullptr;
+  nlk::DevMesh dm{};
+  nlk_params prm{};
+  cudaStream_t st = nullptr;
+  int device = 0;
+  nlk::Nccl nccl;
+  std::vector<nlk::DevNeighbor> neigh;
+  std::vector<void*> allocs;             // everything cudaMalloc'ed, freed in destroy
+  // scalars
+  nlk::SolverScal* d_sc = nullptr;       // device
+  nlk::SolverScal* h_sc = nullptr;       // pinned mirror
+  double* d_red = nullptr;               // device scratch scalars [64 + lgmres]
+  double* h_red = nullptr;               // pinned mirror
+  nlk::Reducer red{};
+  // coordinates (rand field) and misc
+  double* xyz[3] = {nullptr, nullptr, nullptr};
+  int64_t* d_lglel = nullptr;
+  double* ones2 = nullptr;               // N2 ones
+  double* filterF = nullptr;             // n x n
+  // base flow and perturbation state (Nek vx..t / vxp..tp)
+  double* U[3] = {nullptr, nullptr, nullptr};
+  double* T = nullptr;
+  double* vp[3] = {nullptr, nullptr, nullptr};
+  double* prp = nullptr;
+  double* tp = nullptr;
+  double* vlag[2][3] = {{nullptr}};
+  double* exx1[3] = {nullptr}, *exx2[3] = {nullptr};
+  double* prlag = nullptr;
+  double* tlag[2] = {nullptr, nullptr};
+  double* vgradt1 = nullptr, *vgradt2 = nullptr;
+  double* bf[3] = {nullptr}, *bq = nullptr;
+  double* forcing[3] = {nullptr, nullptr, nullptr};
+  bool has_forcing = false;
+  // work
+  double* wk[8] = {nullptr};             // N1 each
+  double* cg_x = nullptr, *cg_r = nullptr, *cg_p = nullptr, *cg_w = nullptr;
+  double* pw[6] = {nullptr};             // N2 each
+  double* gm_V = nullptr, *gm_Z = nullptr;   // (lgmres+1) x N2, lgmres x N2
+  double* sw_w = nullptr, *sw_z = nullptr, *sw_t = nullptr;   // Schwarz work (N1)
+  double* crs_part = nullptr, *crs_r = nullptr, *crs_y = nullptr;
+  bool have_coarse = false, have_schwarz = false;
+  // pressure projection (residualProj)
+  double* proj_X = nullptr, *proj_EX = nullptr; int nproj = 0;
+  // time stepping
+  double dt = 0; int nsteps = 0; bool adjoint = false;
+  // statistics
+  long cg_iters = 0, gmres_iters = 0, steps = 0;
+};
+
+struct nlk_vec {
+  nlk_ctx* c = nullptr;
+  double* v[3] = {nullptr, nullptr, nullptr};
+  double* pr = nullptr;
+  double* theta = nullptr;
+  int nrst = 0;
+  double* rv[2][3] = {{nullptr}};        // rst slots allocated lazily
+  double* rpr[2] = {nullptr, nullptr};
+  double* rth[2] = {nullptr, nullptr};
+};
+
+struct nlk_op {
+  nlk_ctx* c = nullptr;
+  double tau = 1.0;
+  nlk_vec* baseflow = nullptr;           // owned copy
+  nlk_stats stats{};
+};
+
+namespace nlk {
+// internal API shared between translation units
+int ctx_gs(nlk_ctx* c, Ptr3 f, int nf);                                   // full dssum (local + neighbour exchange)
+int ctx_allreduce(nlk_ctx* c, double* d_ptr, int count, bool maxop);
+int ctx_read_scalars(nlk_ctx* c, int count);                              // d_red[0..count) -> h_red, synchronises
+int vec_alloc_rst(nlk_vec* v, int slot);
+int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose);
+int step_setup(nlk_ctx* c, double tau, bool transpose);
+int step_advance(nlk_ctx* c, int istep);
+int helmholtz_solve(nlk_ctx* c, double* rhs_local, double h1, double h2, const double* mask, double tol, double* x, int* iters);
+int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* iters);
+int apply_E(nlk_ctx* c, const double* p, double* ep);
+int apply_precond(nlk_ctx* c, const double* r, double* z);
+int ortho(nlk_ctx* c, double* p);
+int reset_history_pub(nlk_ctx* c);
+void make_filter_matrix(const Basis& b, double w, double cutoff, std::vector<double>& F);
+void make_fdm_1d(const Basis& b, double lm, double ll, double lr, int bcl, int bcr, double* S, double* lam, int* nact);
+double mesh_diag_local(const HostMesh& hm, int64_t e, int p);
+std::vector<double> mat_transpose(const std::vector<double>& M, int r, int cdim);
+template <class T> int dev_alloc(nlk_ctx* c, T** p, size_t count, bool zero = true) {
+  void* q = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  if (e != cudaSuccess) { set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e)); return 1; }
+  if (zero) cudaMemsetAsync(q, 0, count * sizeof(T), c->st);
+  c->allocs.push_back(q); *p = (T*)q; return 0;
+}
+template <class T> int dev_upload(nlk_ctx* c, T** p, const std::vector<T>& h) {
+  if (dev_alloc(c, p, h.size(), false)) return 1;
+  if (!h.empty()) NLK_CUDA(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->st));
+  NLK_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+}  // namespace nlk

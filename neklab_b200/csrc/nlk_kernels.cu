@@ -1,0 +1,903 @@
+// Hand-written sm_100a FP64 CUDA kernels of the exptA hot path.
+// All kernels are HBM/latency-bound integer+FP64 streaming or small tensor contractions: no tensor cores.
+// Element data is staged in shared memory; 1-D operator matrices are staged in shared memory per CTA.
+#include "nlk_device.cuh"
+
+namespace nlk {
+
+thread_local long g_launches = 0;
+#define LAUNCH_COUNT() (++g_launches)
+
+static inline int cdiv(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+static const int RED_BLOCKS = 592;   // 148 SMs x 4
+static const int RED_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------ reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Deterministic two-stage reduction: every block writes its partial sums; the last block to finish (ticket
+// counter) sums the partials in a fixed order.  Returns true on thread 0 of the last block with v[] = totals.
+template <int NV, bool MAXOP = false>
+__device__ bool grid_reduce(double (&v)[NV], Reducer red) {
+  __shared__ double s_part[NV][32];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double t = MAXOP ? warp_max(v[k]) : warp_sum(v[k]);
+    if (lane == 0) s_part[k][wid] = t;
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double t = lane < nw ? s_part[k][lane] : (MAXOP ? -1e300 : 0.0);
+      t = MAXOP ? warp_max(t) : warp_sum(t);
+      if (lane == 0) red.partial[(size_t)k * red.maxblocks + blockIdx.x] = t;
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int ticket = atomicAdd(red.counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double acc = MAXOP ? -1e300 : 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      double t = __ldcg(&red.partial[(size_t)k * red.maxblocks + b]);
+      acc = MAXOP ? fmax(acc, t) : acc + t;
+    }
+    acc = MAXOP ? warp_max(acc) : warp_sum(acc);
+    __syncthreads();
+    if (lane == 0) s_part[k][wid] = acc;
+    __syncthreads();
+    if (wid == 0) {
+      double t = lane < nw ? s_part[k][lane] : (MAXOP ? -1e300 : 0.0);
+      t = MAXOP ? warp_max(t) : warp_sum(t);
+      v[k] = t;
+    }
+  }
+  if (threadIdx.x == 0) *red.counter = 0u;
+  return threadIdx.x == 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 axhelm
+// One element per (threadIdx.y) slice; thread (i,j) owns the k-column of the element (register-tiled k-loop, 3-D).
+// FUSE_CG: the CG search-direction update p = r/(h1*diagA+h2*diagB) + beta*p is applied while loading.
+template <int N, int DIM, bool FUSE_CG>
+__global__ void __launch_bounds__(N * N * (N * N >= 100 ? 1 : (N * N >= 64 ? 2 : 4)))
+k_axhelm(const double* __restrict__ u, double* __restrict__ pio, const double* __restrict__ r, double* __restrict__ w,
+         const double* __restrict__ G, const double* __restrict__ bm1, const double* __restrict__ Dg,
+         const double* __restrict__ diagA, const double* __restrict__ diagB, double h1, double h2,
+         const SolverScal* __restrict__ sc, int64_t E) {
+  constexpr int NZ = DIM == 3 ? N : 1;
+  constexpr int NN = N * N;
+  constexpr int NP = NN * NZ;
+  constexpr int NG = DIM == 3 ? 6 : 3;
+  constexpr int EPB = NN >= 100 ? 1 : (NN >= 64 ? 2 : 4);
+  __shared__ double sD[NN], sDt[NN];
+  __shared__ double s_u[EPB][NN], s_gr[EPB][NN], s_gs[EPB][NN];
+  if (FUSE_CG && sc->done) return;
+  const int tid = threadIdx.x, le = threadIdx.y;
+  const int64_t e = (int64_t)blockIdx.x * EPB + le;
+  const int i = tid % N, j = tid / N;
+  for (int idx = tid + le * NN; idx < NN; idx += NN * EPB) { double v = Dg[idx]; sD[idx] = v; sDt[(idx % N) * N + idx / N] = v; }
+  const bool active = e < E;
+  double ru[NZ], rw[NZ];
+  const size_t eb = (size_t)(active ? e : 0) * NP;
+  if (FUSE_CG) {
+    const double beta = sc->beta;
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) {
+      size_t g = eb + k * NN + tid;
+      double z = r[g] / (h1 * diagA[g] + h2 * diagB[g]);
+      double pv = z + beta * pio[g];
+      ru[k] = active ? pv : 0.0;
+      if (active) pio[g] = pv;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) ru[k] = active ? u[eb + k * NN + tid] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < NZ; ++k) rw[k] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NZ; ++k) {
+    s_u[le][tid] = ru[k];
+    __syncthreads();
+    double ur = 0, us = 0, ut = 0;
+#pragma unroll
+    for (int l = 0; l < N; ++l) {
+      ur += sDt[l * N + i] * s_u[le][j * N + l];
+      us += sD[j * N + l] * s_u[le][l * N + i];
+    }
+    if (DIM == 3) {
+#pragma unroll
+      for (int l = 0; l < N; ++l) ut += sD[k * N + l] * ru[l];
+    }
+    const size_t gb = (size_t)(active ? e : 0) * NG * NP + k * NN + tid;
+    double gr, gs, gt = 0;
+    if (DIM == 3) {
+      double g11 = G[gb], g22 = G[gb + NP], g33 = G[gb + 2 * NP], g12 = G[gb + 3 * NP], g13 = G[gb + 4 * NP], g23 = G[gb + 5 * NP];
+      gr = g11 * ur + g12 * us + g13 * ut;
+      gs = g12 * ur + g22 * us + g23 * ut;
+      gt = g13 * ur + g23 * us + g33 * ut;
+    } else {
+      double g11 = G[gb], g22 = G[gb + NP], g12 = G[gb + 2 * NP];
+      gr = g11 * ur + g12 * us;
+      gs = g12 * ur + g22 * us;
+    }
+    s_gr[le][tid] = gr; s_gs[le][tid] = gs;
+    __syncthreads();
+    double acc = 0;
+#pragma unroll
+    for (int l = 0; l < N; ++l) acc += sD[l * N + i] * s_gr[le][j * N + l] + sD[l * N + j] * s_gs[le][l * N + i];
+    rw[k] += acc;
+    if (DIM == 3) {
+#pragma unroll
+      for (int l = 0; l < N; ++l) rw[l] += sD[k * N + l] * gt;
+    }
+    __syncthreads();
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) { size_t g = eb + k * NN + tid; w[g] = h1 * rw[k] + h2 * bm1[g] * ru[k]; }
+  }
+}
+
+template <int N, int DIM>
+static void axhelm_dispatch(const DevMesh& dm, const double* u, double* pio, const double* r, double* w, double h1, double h2,
+                            const SolverScal* sc, bool fuse, cudaStream_t st) {
+  constexpr int EPB = N * N >= 100 ? 1 : (N * N >= 64 ? 2 : 4);
+  dim3 block(N * N, EPB), grid(cdiv(dm.E, EPB));
+  if (fuse) k_axhelm<N, DIM, true><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, dm.diagA, dm.diagB, h1, h2, sc, dm.E);
+  else k_axhelm<N, DIM, false><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, dm.diagA, dm.diagB, h1, h2, sc, dm.E);
+  LAUNCH_COUNT();
+}
+
+#define NLK_FOR_N(FN, ...)                                                    \
+  switch (dm.n * 10 + dm.ndim) {                                              \
+    case 42: FN<4, 2>(__VA_ARGS__); break;   case 43: FN<4, 3>(__VA_ARGS__); break;   \
+    case 52: FN<5, 2>(__VA_ARGS__); break;   case 53: FN<5, 3>(__VA_ARGS__); break;   \
+    case 62: FN<6, 2>(__VA_ARGS__); break;   case 63: FN<6, 3>(__VA_ARGS__); break;   \
+    case 72: FN<7, 2>(__VA_ARGS__); break;   case 73: FN<7, 3>(__VA_ARGS__); break;   \
+    case 82: FN<8, 2>(__VA_ARGS__); break;   case 83: FN<8, 3>(__VA_ARGS__); break;   \
+    case 92: FN<9, 2>(__VA_ARGS__); break;   case 93: FN<9, 3>(__VA_ARGS__); break;   \
+    case 102: FN<10, 2>(__VA_ARGS__); break; case 103: FN<10, 3>(__VA_ARGS__); break; \
+    case 112: FN<11, 2>(__VA_ARGS__); break; case 113: FN<11, 3>(__VA_ARGS__); break; \
+    case 122: FN<12, 2>(__VA_ARGS__); break; case 123: FN<12, 3>(__VA_ARGS__); break; \
+    default: break;                                                           \
+  }
+
+void launch_axhelm(const DevMesh& dm, const double* u, double* w, double h1, double h2, cudaStream_t st) {
+  NLK_FOR_N(axhelm_dispatch, dm, u, nullptr, nullptr, w, h1, h2, nullptr, false, st)
+}
+void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, double h1, double h2, const SolverScal* sc, cudaStream_t st) {
+  NLK_FOR_N(axhelm_dispatch, dm, p, p, r, w, h1, h2, sc, true, st)
+}
+
+// ------------------------------------------------------------------------------------------------ K2 dssum
+__global__ void k_gs(Ptr3 f, int nf, const int32_t* __restrict__ off, const int32_t* __restrict__ idx, int ngs) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ngs) return;
+  const int b = off[g], e = off[g + 1];
+  for (int c = 0; c < nf; ++c) {
+    double* u = f.p[c];
+    double s = 0;
+    for (int t = b; t < e; ++t) s += u[idx[t]];
+    for (int t = b; t < e; ++t) u[idx[t]] = s;
+  }
+}
+void launch_gs(const DevMesh& dm, Ptr3 f, int nf, cudaStream_t st) {
+  if (dm.ngs == 0) return;
+  k_gs<<<cdiv(dm.ngs, 128), 128, 0, st>>>(f, nf, dm.gs_off, dm.gs_idx, dm.ngs);
+  LAUNCH_COUNT();
+}
+
+__global__ void k_pack(const double* __restrict__ u, const int32_t* __restrict__ rep, int cnt, double* __restrict__ buf) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < cnt) buf[t] = u[rep[t]];
+}
+void launch_pack(const double* u, const int32_t* rep, int cnt, double* buf, cudaStream_t st) {
+  if (!cnt) return;
+  k_pack<<<cdiv(cnt, 128), 128, 0, st>>>(u, rep, cnt, buf); LAUNCH_COUNT();
+}
+__global__ void k_unpack_add(double* __restrict__ u, const int32_t* __restrict__ off, const int32_t* __restrict__ idx, int cnt,
+                             const double* __restrict__ buf) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  double v = buf[t];
+  for (int s = off[t]; s < off[t + 1]; ++s) u[idx[s]] += v;
+}
+void launch_unpack_add(double* u, const int32_t* off, const int32_t* idx, int cnt, const double* buf, cudaStream_t st) {
+  if (!cnt) return;
+  k_unpack_add<<<cdiv(cnt, 128), 128, 0, st>>>(u, off, idx, cnt, buf); LAUNCH_COUNT();
+}
+
+// ------------------------------------------------------------------------------------------------ pointwise
+__global__ void k_lin(double* __restrict__ out, size_t n, double a0, const double* __restrict__ x0, double a1, const double* __restrict__ x1,
+                      double a2, const double* __restrict__ x2, double a3, const double* __restrict__ x3, const double* __restrict__ mul) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double v = 0;
+    if (x0) v += a0 * x0[i];
+    if (x1) v += a1 * x1[i];
+    if (x2) v += a2 * x2[i];
+    if (x3) v += a3 * x3[i];
+    if (mul) v *= mul[i];
+    out[i] = v;
+  }
+}
+void launch_lin(double* out, size_t n, double a0, const double* x0, double a1, const double* x1, double a2, const double* x2, double a3,
+                const double* x3, const double* mul, cudaStream_t st) {
+  if (!n) return;
+  int grid = std::min(cdiv(n, 256), 148 * 16);
+  k_lin<<<grid, 256, 0, st>>>(out, n, a0, x0, a1, x1, a2, x2, a3, x3, mul); LAUNCH_COUNT();
+}
+__global__ void k_axpy_mm(double* __restrict__ out, size_t n, const double* __restrict__ x0, double a, const double* __restrict__ x1,
+                          const double* __restrict__ m1, const double* __restrict__ m2) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double v = a * x1[i] * m1[i];
+    if (m2) v *= m2[i];
+    out[i] = (x0 ? x0[i] : 0.0) + v;
+  }
+}
+void launch_axpy_mm(double* out, size_t n, const double* x0, double a, const double* x1, const double* m1, const double* m2, cudaStream_t st) {
+  k_axpy_mm<<<std::min(cdiv(n, 256), 148 * 16), 256, 0, st>>>(out, n, x0, a, x1, m1, m2); LAUNCH_COUNT();
+}
+__global__ void k_fill(double* out, size_t n, double v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = v;
+}
+void launch_fill(double* out, size_t n, double v, cudaStream_t st) {
+  if (!n) return;
+  k_fill<<<std::min(cdiv(n, 256), 148 * 16), 256, 0, st>>>(out, n, v); LAUNCH_COUNT();
+}
+__global__ void k_sub_mean(double* p, size_t n, const double* sum, double inv_count) {
+  const double mean = *sum * inv_count;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] -= mean;
+}
+void launch_sub_mean(double* p, size_t n, const double* sum, double inv_count, cudaStream_t st) {
+  k_sub_mean<<<std::min(cdiv(n, 256), 148 * 16), 256, 0, st>>>(p, n, sum, inv_count); LAUNCH_COUNT();
+}
+
+// ------------------------------------------------------------------------------------------------ generic smem contraction
+// out = M (mo x mi, row-major) applied along direction dir of `in` with dims (n0 x fastest, n1, n2); block-strided.
+template <bool ACC>
+__device__ __forceinline__ void contract(double* __restrict__ out, const double* __restrict__ in, const double* __restrict__ M, int mo,
+                                         int mi, int dir, int n0, int n1, int n2) {
+  const int o0 = dir == 0 ? mo : n0, o1 = dir == 1 ? mo : n1, o2 = dir == 2 ? mo : n2;
+  const int tot = o0 * o1 * o2;
+  const int stride = dir == 0 ? 1 : (dir == 1 ? n0 : n0 * n1);
+  for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+    const int i = idx % o0, j = (idx / o0) % o1, k = idx / (o0 * o1);
+    const int r = dir == 0 ? i : (dir == 1 ? j : k);
+    const int base = (dir == 0 ? 0 : i) + n0 * ((dir == 1 ? 0 : j) + n1 * (dir == 2 ? 0 : k));
+    const double* Mr = M + r * mi;
+    double s = 0;
+    for (int l = 0; l < mi; ++l) s += Mr[l] * in[base + l * stride];
+    if (ACC) out[idx] += s; else out[idx] = s;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void load_mat(double* s, const double* g, int cnt) {
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) s[i] = g[i];
+}
+
+// ------------------------------------------------------------------------------------------------ K5 opdiv / opgradt
+// p = scale * sum_c sum_k rxw2[k][c] * (d_k u_c)|GL     (Nek multd / opdiv); one element per CTA.
+__global__ void k_opdiv(CPtr3 u, double* __restrict__ p, const double* __restrict__ rxw2, const double* __restrict__ I12g,
+                        const double* __restrict__ D12g, int n, int q, int d, double scale) {
+  extern __shared__ double sm[];
+  const int nz = d == 3 ? n : 1, qz = d == 3 ? q : 1;
+  const int np1 = n * n * nz, np2 = q * q * qz;
+  double* sI = sm; double* sDm = sI + q * n;
+  double* U = sDm + q * n; double* A = U + np1; double* B = A + np1; double* T0 = B + np1; double* T1 = T0 + np1; double* T2 = T1 + np1;
+  double* acc = T2 + np1;
+  const size_t e = blockIdx.x;
+  load_mat(sI, I12g, q * n); load_mat(sDm, D12g, q * n);
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) acc[i] = 0.0;
+  __syncthreads();
+  for (int c = 0; c < d; ++c) {
+    const double* uc = u.p[c] + e * np1;
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) U[i] = uc[i];
+    __syncthreads();
+    contract<false>(A, U, sDm, q, n, 0, n, n, nz);      // D_x u   (q,n,nz)
+    contract<false>(B, U, sI, q, n, 0, n, n, nz);       // I_x u
+    const double* rw = rxw2 + e * (size_t)(d * d) * np2;
+    if (d == 2) {
+      contract<false>(T0, A, sI, q, n, 1, q, n, 1);     // d/dr
+      contract<false>(T1, B, sDm, q, n, 1, q, n, 1);    // d/ds
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) acc[i] += rw[(0 * d + c) * np2 + i] * T0[i] + rw[(1 * d + c) * np2 + i] * T1[i];
+      __syncthreads();
+    } else {
+      contract<false>(T0, A, sI, q, n, 1, q, n, n);     // I_y D_x u  (q,q,n)
+      contract<false>(T1, B, sDm, q, n, 1, q, n, n);    // D_y I_x u
+      contract<false>(T2, B, sI, q, n, 1, q, n, n);     // I_y I_x u
+      contract<false>(A, T0, sI, q, n, 2, q, q, n);     // d/dr
+      contract<false>(B, T1, sI, q, n, 2, q, q, n);     // d/ds
+      contract<false>(U, T2, sDm, q, n, 2, q, q, n);    // d/dt
+      for (int i = threadIdx.x; i < np2; i += blockDim.x)
+        acc[i] += rw[(0 * d + c) * np2 + i] * A[i] + rw[(1 * d + c) * np2 + i] * B[i] + rw[(2 * d + c) * np2 + i] * U[i];
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) p[e * np2 + i] = scale * acc[i];
+}
+static int elem_threads(int np) { int t = ((np + 31) / 32) * 32; return t > 256 ? 256 : (t < 64 ? 64 : t); }
+
+void launch_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, cudaStream_t st) {
+  size_t smem = (size_t)(2 * dm.q * dm.n + 7 * dm.np1) * sizeof(double);
+  static size_t set = 0;
+  if (smem > 48 * 1024 && smem > set) { cudaFuncSetAttribute(k_opdiv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
+  k_opdiv<<<(unsigned)dm.E, elem_threads(dm.np1), smem, st>>>(u, p, dm.rxw2, dm.I12, dm.D12, dm.n, dm.q, dm.ndim, scale);
+  LAUNCH_COUNT();
+}
+
+// w_c = sum_k (transposed interp/deriv)[ p * rxw2[k][c] ]    (Nek cdtp / opgradt)
+__global__ void k_opgradt(const double* __restrict__ p, Ptr3 w, const double* __restrict__ rxw2, const double* __restrict__ I12tg,
+                          const double* __restrict__ D12tg, int n, int q, int d) {
+  extern __shared__ double sm[];
+  const int nz = d == 3 ? n : 1, qz = d == 3 ? q : 1;
+  const int np1 = n * n * nz, np2 = q * q * qz;
+  double* sIt = sm; double* sDt = sIt + q * n;
+  double* P = sDt + q * n; double* S0 = P + np1; double* S1 = S0 + np1; double* S2 = S1 + np1; double* A0 = S2 + np1; double* A1 = A0 + np1;
+  double* A2 = A1 + np1;
+  const size_t e = blockIdx.x;
+  load_mat(sIt, I12tg, q * n); load_mat(sDt, D12tg, q * n);
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) P[i] = p[e * np2 + i];
+  __syncthreads();
+  const double* rw = rxw2 + e * (size_t)(d * d) * np2;
+  for (int c = 0; c < d; ++c) {
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+      S0[i] = P[i] * rw[(0 * d + c) * np2 + i];
+      S1[i] = P[i] * rw[(1 * d + c) * np2 + i];
+      if (d == 3) S2[i] = P[i] * rw[(2 * d + c) * np2 + i];
+    }
+    __syncthreads();
+    double* wc = w.p[c] + e * np1;
+    if (d == 2) {
+      contract<false>(A0, S0, sDt, n, q, 0, q, q, 1);   // D^T_x  (n,q)
+      contract<false>(A1, S1, sIt, n, q, 0, q, q, 1);   // I^T_x
+      contract<false>(S0, A0, sIt, n, q, 1, n, q, 1);   // I^T_y
+      contract<true>(S0, A1, sDt, n, q, 1, n, q, 1);    // + D^T_y
+      for (int i = threadIdx.x; i < np1; i += blockDim.x) wc[i] = S0[i];
+      __syncthreads();
+    } else {
+      contract<false>(A0, S0, sDt, n, q, 0, q, q, q);   // (n,q,q)
+      contract<false>(A1, S1, sIt, n, q, 0, q, q, q);
+      contract<false>(A2, S2, sIt, n, q, 0, q, q, q);
+      contract<false>(S0, A0, sIt, n, q, 1, n, q, q);   // (n,n,q)
+      contract<true>(S0, A1, sDt, n, q, 1, n, q, q);
+      contract<false>(S1, A2, sIt, n, q, 1, n, q, q);
+      contract<false>(A0, S0, sIt, n, q, 2, n, n, q);   // (n,n,n)
+      contract<true>(A0, S1, sDt, n, q, 2, n, n, q);
+      for (int i = threadIdx.x; i < np1; i += blockDim.x) wc[i] = A0[i];
+      __syncthreads();
+    }
+  }
+}
+void launch_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st) {
+  size_t smem = (size_t)(2 * dm.q * dm.n + 7 * dm.np1) * sizeof(double);
+  static size_t set = 0;
+  if (smem > 48 * 1024 && smem > set) { cudaFuncSetAttribute(k_opgradt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
+  k_opgradt<<<(unsigned)dm.E, elem_threads(dm.np1), smem, st>>>(p, w, dm.rxw2, dm.I12t, dm.D12t, dm.n, dm.q, dm.ndim);
+  LAUNCH_COUNT();
+}
+
+// ------------------------------------------------------------------------------------------------ K3/K4 convection
+// out_f (+)= alpha * I^T [ sum_k (sum_c rxd[k][c] * I C_c) * D_k (I u_f) ]   -- Nek convect_new, ifcf=.false.
+__global__ void k_convect(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __restrict__ rxd, const double* __restrict__ I1dg,
+                          const double* __restrict__ I1dtg, const double* __restrict__ Ddg, int n, int m, int d, double alpha,
+                          int accumulate) {
+  extern __shared__ double sm[];
+  const int nz = d == 3 ? n : 1, mz = d == 3 ? m : 1;
+  const int np1 = n * n * nz, npd = m * m * mz;
+  double* sI = sm; double* sIt = sI + m * n; double* sDd = sIt + m * n;
+  double* TR = sDd + m * m;             // d * npd
+  double* UF = TR + 3 * npd;            // npd
+  double* W1 = UF + npd;                // npd (scratch)
+  double* W2 = W1 + npd;                // npd (scratch)
+  double* ACC = W2 + npd;               // npd
+  const size_t e = blockIdx.x;
+  load_mat(sI, I1dg, m * n); load_mat(sIt, I1dtg, m * n); load_mat(sDd, Ddg, m * m);
+  __syncthreads();
+  // interpolate the convecting field, then tr_k = sum_c rxd[k][c] * Cf_c (in place, pointwise)
+  for (int c = 0; c < d; ++c) {
+    const double* cc = C.p[c] + e * np1;
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = cc[i];
+    __syncthreads();
+    if (d == 2) {
+      contract<false>(W2, W1, sI, m, n, 0, n, n, 1);
+      contract<false>(TR + c * npd, W2, sI, m, n, 1, m, n, 1);
+    } else {
+      contract<false>(W2, W1, sI, m, n, 0, n, n, n);
+      contract<false>(W1, W2, sI, m, n, 1, m, n, n);
+      contract<false>(TR + c * npd, W1, sI, m, n, 2, m, m, n);
+    }
+  }
+  const double* rx = rxd + e * (size_t)(d * d) * npd;
+  for (int i = threadIdx.x; i < npd; i += blockDim.x) {
+    double cf[3] = {TR[i], TR[npd + i], d == 3 ? TR[2 * npd + i] : 0.0};
+    for (int k = 0; k < d; ++k) {
+      double s = 0;
+      for (int c = 0; c < d; ++c) s += rx[(k * d + c) * npd + i] * cf[c];
+      TR[k * npd + i] = s;
+    }
+  }
+  __syncthreads();
+  for (int f = 0; f < nf; ++f) {
+    const double* uf = u.p[f] + e * np1;
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = uf[i];
+    __syncthreads();
+    if (d == 2) {
+      contract<false>(W2, W1, sI, m, n, 0, n, n, 1);
+      contract<false>(UF, W2, sI, m, n, 1, m, n, 1);
+      contract<false>(W1, UF, sDd, m, m, 0, m, m, 1);
+      contract<false>(W2, UF, sDd, m, m, 1, m, m, 1);
+      for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] = TR[i] * W1[i] + TR[npd + i] * W2[i];
+      __syncthreads();
+      contract<false>(W1, ACC, sIt, n, m, 0, m, m, 1);
+      contract<false>(W2, W1, sIt, n, m, 1, n, m, 1);
+    } else {
+      contract<false>(W2, W1, sI, m, n, 0, n, n, n);
+      contract<false>(W1, W2, sI, m, n, 1, m, n, n);
+      contract<false>(UF, W1, sI, m, n, 2, m, m, n);
+      contract<false>(W1, UF, sDd, m, m, 0, m, m, m);
+      for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] = TR[i] * W1[i];
+      __syncthreads();
+      contract<false>(W1, UF, sDd, m, m, 1, m, m, m);
+      for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] += TR[npd + i] * W1[i];
+      __syncthreads();
+      contract<false>(W1, UF, sDd, m, m, 2, m, m, m);
+      for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] += TR[2 * npd + i] * W1[i];
+      __syncthreads();
+      contract<false>(W1, ACC, sIt, n, m, 0, m, m, m);
+      contract<false>(UF, W1, sIt, n, m, 1, n, m, m);
+      contract<false>(W2, UF, sIt, n, m, 2, n, n, m);
+    }
+    double* of = out.p[f] + e * np1;
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[i];
+    __syncthreads();
+  }
+}
+void launch_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double alpha, int accumulate, cudaStream_t st) {
+  size_t smem = (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * dm.npd) * sizeof(double);
+  static size_t set = 0;
+  if (smem > 48 * 1024 && smem > set) { cudaFuncSetAttribute(k_convect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
+  k_convect<<<(unsigned)dm.E, elem_threads(dm.npd), smem, st>>>(u, nf, C, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, dm.n, dm.m, dm.ndim, alpha, accumulate);
+  LAUNCH_COUNT();
+}
+
+// out_i (+)= alpha * I^T [ sum_j (I c_j) * sum_k rxd[k][i] D_k (I U_j) ]   -- Nek convect_adj
+__global__ void k_convect_adj(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __restrict__ rxd, const double* __restrict__ I1dg,
+                              const double* __restrict__ I1dtg, const double* __restrict__ Ddg, int n, int m, int d, double alpha,
+                              int accumulate) {
+  extern __shared__ double sm[];
+  const int nz = d == 3 ? n : 1, mz = d == 3 ? m : 1;
+  const int np1 = n * n * nz, npd = m * m * mz;
+  double* sI = sm; double* sIt = sI + m * n; double* sDd = sIt + m * n;
+  double* AC = sDd + m * m;             // d * npd accumulators
+  double* UF = AC + 3 * npd; double* W1 = UF + npd; double* W2 = W1 + npd; double* CF = W2 + npd;
+  const size_t e = blockIdx.x;
+  load_mat(sI, I1dg, m * n); load_mat(sIt, I1dtg, m * n); load_mat(sDd, Ddg, m * m);
+  for (int i = threadIdx.x; i < d * npd; i += blockDim.x) AC[i] = 0.0;
+  __syncthreads();
+  const double* rx = rxd + e * (size_t)(d * d) * npd;
+  for (int j = 0; j < d; ++j) {
+    // CF = I c_j ; UF = I U_j
+    for (int pass = 0; pass < 2; ++pass) {
+      const double* src = (pass == 0 ? cf.p[j] : U.p[j]) + e * np1;
+      double* dst = pass == 0 ? CF : UF;
+      for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = src[i];
+      __syncthreads();
+      if (d == 2) { contract<false>(W2, W1, sI, m, n, 0, n, n, 1); contract<false>(dst, W2, sI, m, n, 1, m, n, 1); }
+      else { contract<false>(W2, W1, sI, m, n, 0, n, n, n); contract<false>(W1, W2, sI, m, n, 1, m, n, n); contract<false>(dst, W1, sI, m, n, 2, m, m, n); }
+    }
+    for (int k = 0; k < d; ++k) {
+      contract<false>(W1, UF, sDd, m, m, k, m, m, mz);
+      for (int i = threadIdx.x; i < npd; i += blockDim.x) {
+        double g = CF[i] * W1[i];
+        for (int c = 0; c < d; ++c) AC[c * npd + i] += rx[(k * d + c) * npd + i] * g;
+      }
+      __syncthreads();
+    }
+  }
+  for (int c = 0; c < d; ++c) {
+    if (d == 2) { contract<false>(W1, AC + c * npd, sIt, n, m, 0, m, m, 1); contract<false>(W2, W1, sIt, n, m, 1, n, m, 1); }
+    else { contract<false>(W1, AC + c * npd, sIt, n, m, 0, m, m, m); contract<false>(UF, W1, sIt, n, m, 1, n, m, m); contract<false>(W2, UF, sIt, n, m, 2, n, n, m); }
+    double* of = out.p[c] + e * np1;
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[i];
+    __syncthreads();
+  }
+}
+void launch_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st) {
+  size_t smem = (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * dm.npd) * sizeof(double);
+  static size_t set = 0;
+  if (smem > 48 * 1024 && smem > set) { cudaFuncSetAttribute(k_convect_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
+  k_convect_adj<<<(unsigned)dm.E, elem_threads(dm.npd), smem, st>>>(U, c, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, dm.n, dm.m, dm.ndim, alpha, accumulate);
+  LAUNCH_COUNT();
+}
+
+// ------------------------------------------------------------------------------------------------ K7 rhs tail
+// makextp + makebdfp + lagfieldp fused, all components in one launch (blockIdx.y = component).
+__global__ void k_rhs_tail(RhsTail t, size_t n, const double* __restrict__ bm1, double ab0, double ab1, double ab2, double bd1, double bd2,
+                           double bd3) {
+  const int f = blockIdx.y;
+  double* bf = t.bf[f]; double* e1 = t.e1[f]; double* e2 = t.e2[f]; const double* u = t.u[f]; double* l1 = t.lag1[f]; double* l2 = t.lag2[f];
+  const double coef = t.coef[f];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double b = bf[i], x1 = e1[i], x2 = e2[i], uu = u[i], a1 = l1[i], a2 = l2[i];
+    e2[i] = x1; e1[i] = b;
+    bf[i] = ab0 * b + ab1 * x1 + ab2 * x2 + coef * bm1[i] * (bd1 * uu + bd2 * a1 + bd3 * a2);
+    l2[i] = a1; l1[i] = uu;
+  }
+}
+void launch_rhs_tail(const DevMesh& dm, const RhsTail& t, int nf, double ab0, double ab1, double ab2, double bd1, double bd2, double bd3,
+                     cudaStream_t st) {
+  dim3 grid(std::min(cdiv(dm.N1, 256), 148 * 8), nf);
+  k_rhs_tail<<<grid, 256, 0, st>>>(t, dm.N1, dm.bm1, ab0, ab1, ab2, bd1, bd2, bd3); LAUNCH_COUNT();
+}
+
+// ------------------------------------------------------------------------------------------------ K8 CG vector phases
+// Nek cggo scalar logic: convergence test on rbn2 = sqrt(sum r^2 mult binv / vol), beta = rtz1/rtz2.
+__device__ __forceinline__ void cg_finalize_zr(SolverScal* sc, double vol) {
+  double v0 = sc->red[0], v1 = sc->red[1];
+  sc->rtz2 = sc->rtz1; sc->rtz1 = v0;
+  double rbn2 = sqrt(v1 / vol);
+  sc->rbn2 = rbn2;
+  if (sc->iter == 0) sc->rbn0 = rbn2;
+  if (rbn2 <= sc->tol || sc->iter >= sc->maxit || !(v0 == v0)) { sc->done = 1; }
+  else { sc->beta = sc->iter == 0 ? 0.0 : v0 / sc->rtz2; sc->iter += 1; }
+}
+__device__ __forceinline__ void cg_finalize_pap(SolverScal* sc) { sc->pap = sc->red[2]; sc->alpha = sc->rtz1 / sc->red[2]; }
+__global__ void k_cg_finalize(SolverScal* sc, int which, double vol) {
+  if (sc->done) return;
+  if (which == 0) cg_finalize_zr(sc, vol); else cg_finalize_pap(sc);
+}
+void launch_cg_finalize(SolverScal* sc, int which, double vol, cudaStream_t st) { k_cg_finalize<<<1, 1, 0, st>>>(sc, which, vol); LAUNCH_COUNT(); }
+__global__ void k_recip(double* __restrict__ out, const double* __restrict__ x, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = 1.0 / x[i];
+}
+void launch_recip(double* out, const double* x, size_t n, cudaStream_t st) {
+  k_recip<<<std::min(cdiv(n, 256), 148 * 16), 256, 0, st>>>(out, x, n); LAUNCH_COUNT();
+}
+__global__ void k_cg_init(SolverScal* sc, double tol, int maxit) {
+  sc->rtz1 = 1.0; sc->rtz2 = 1.0; sc->rbn2 = 0; sc->rbn0 = 0; sc->pap = 0; sc->alpha = 0; sc->beta = 0; sc->tol = tol;
+  sc->iter = 0; sc->done = 0; sc->maxit = maxit;
+}
+void launch_cg_init(const DevMesh&, SolverScal* sc, double tol, int maxit, cudaStream_t st) { k_cg_init<<<1, 1, 0, st>>>(sc, tol, maxit); LAUNCH_COUNT(); }
+
+// x += alpha p ; r -= alpha (mask w)   [skipped when first]; then rtz1 = sum r*z*mult, rbn2 = sum r*r*mult*binv with
+// z = r/(h1 diagA + h2 diagB).  Finaliser applies Nek cggo's convergence test and sets beta.
+__global__ void __launch_bounds__(256)
+k_cg_update_reduce(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ w,
+                   const double* __restrict__ mask, const double* __restrict__ diagA, const double* __restrict__ diagB,
+                   const double* __restrict__ mult, const double* __restrict__ binv, double h1, double h2, double vol, size_t n,
+                   SolverScal* sc, Reducer red, int first, int defer) {
+  if (sc->done) return;
+  const double alpha = first ? 0.0 : sc->alpha;
+  double v[2] = {0.0, 0.0};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double ri = r[i];
+    if (!first) {
+      x[i] += alpha * p[i];
+      ri -= alpha * mask[i] * w[i];
+      r[i] = ri;
+    }
+    double z = ri / (h1 * diagA[i] + h2 * diagB[i]);
+    double m = mult[i];
+    v[0] += ri * z * m;
+    v[1] += ri * ri * m * binv[i];
+  }
+  if (grid_reduce<2>(v, red)) {
+    sc->red[0] = v[0]; sc->red[1] = v[1];
+    if (!defer) cg_finalize_zr(sc, vol);
+  }
+}
+void launch_cg_update_reduce(const DevMesh& dm, double* x, double* r, const double* p, const double* w, const double* mask, double h1,
+                             double h2, SolverScal* sc, Reducer red, int first, int defer, cudaStream_t st) {
+  int grid = std::min(cdiv(dm.N1, RED_THREADS), RED_BLOCKS);
+  k_cg_update_reduce<<<grid, RED_THREADS, 0, st>>>(x, r, p, w, mask, dm.diagA, dm.diagB, dm.vmult, dm.binvm1, h1, h2, dm.volvm1, dm.N1, sc, red, first, defer);
+  LAUNCH_COUNT();
+}
+__global__ void __launch_bounds__(256)
+k_cg_pap(const double* __restrict__ w, const double* __restrict__ p, const double* __restrict__ mask, const double* __restrict__ mult,
+         size_t n, SolverScal* sc, Reducer red, int defer) {
+  if (sc->done) return;
+  double v[1] = {0.0};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[0] += w[i] * mask[i] * p[i] * mult[i];
+  if (grid_reduce<1>(v, red)) { sc->red[2] = v[0]; if (!defer) cg_finalize_pap(sc); }
+}
+void launch_cg_pap(const DevMesh& dm, const double* w, const double* p, const double* mask, SolverScal* sc, Reducer red, int defer, cudaStream_t st) {
+  int grid = std::min(cdiv(dm.N1, RED_THREADS), RED_BLOCKS);
+  k_cg_pap<<<grid, RED_THREADS, 0, st>>>(w, p, mask, dm.vmult, dm.N1, sc, red, defer); LAUNCH_COUNT();
+}
+
+// ------------------------------------------------------------------------------------------------ dots
+__global__ void __launch_bounds__(256)
+k_dot(size_t n, CPtr4 a, CPtr4 b, int npairs, const double* __restrict__ c, double* out, Reducer red) {
+  double v[1] = {0.0};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double s = 0;
+    for (int k = 0; k < npairs; ++k) s += a.p[k][i] * b.p[k][i];
+    v[0] += c ? s * c[i] : s;
+  }
+  if (grid_reduce<1>(v, red)) out[0] = v[0];
+}
+void launch_dot(size_t n, CPtr4 a, CPtr4 b, int npairs, const double* c, double* out, Reducer red, cudaStream_t st) {
+  int grid = std::min(cdiv(n, RED_THREADS), RED_BLOCKS);
+  k_dot<<<grid, RED_THREADS, 0, st>>>(n, a, b, npairs, c, out, red); LAUNCH_COUNT();
+}
+
+// h[j] = sum_i V[j*ld + i] * w[i], j < k <= 32: w is streamed once for all k rows (tall-skinny V^T w).
+template <int KB>
+__global__ void __launch_bounds__(256)
+k_multidot(const double* __restrict__ V, size_t ld, int k0, int k, const double* __restrict__ w, size_t n, double* h, Reducer red) {
+  double v[KB];
+#pragma unroll
+  for (int j = 0; j < KB; ++j) v[j] = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double wi = w[i];
+#pragma unroll
+    for (int j = 0; j < KB; ++j) if (k0 + j < k) v[j] += V[(size_t)(k0 + j) * ld + i] * wi;
+  }
+  if (grid_reduce<KB>(v, red)) {
+    for (int j = 0; j < KB; ++j) if (k0 + j < k) h[k0 + j] = v[j];
+  }
+}
+void launch_multidot(const double* V, size_t ld, int k, const double* w, size_t n, double* h, Reducer red, cudaStream_t st) {
+  int grid = std::min(cdiv(n, RED_THREADS), RED_BLOCKS);
+  for (int k0 = 0; k0 < k; k0 += 8) { k_multidot<8><<<grid, RED_THREADS, 0, st>>>(V, ld, k0, k, w, n, h, red); LAUNCH_COUNT(); }
+}
+__global__ void k_multiaxpy(double* __restrict__ w, const double* __restrict__ V, size_t ld, int k, const double* __restrict__ h, double sign, size_t n) {
+  extern __shared__ double sh[];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) sh[j] = sign * h[j];
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double s = w[i];
+    for (int j = 0; j < k; ++j) s += sh[j] * V[(size_t)j * ld + i];
+    w[i] = s;
+  }
+}
+void launch_multiaxpy(double* w, const double* V, size_t ld, int k, const double* h, double sign, size_t n, cudaStream_t st) {
+  if (k <= 0) return;
+  k_multiaxpy<<<std::min(cdiv(n, 256), 148 * 8), 256, k * sizeof(double), st>>>(w, V, ld, k, h, sign, n); LAUNCH_COUNT();
+}
+
+// ------------------------------------------------------------------------------------------------ K10 Schwarz
+__device__ __forceinline__ int clamp_inner(int i, int n) { return i == 0 ? 1 : (i == n - 1 ? n - 2 : i); }
+
+// w (n^d) <- r (q^d): interior copy; face layers (tangentially interior) = first interior layer; edges/corners = 0
+__global__ void k_schwarz_embed(const double* __restrict__ r, double* __restrict__ w, int n, int d, size_t N1) {
+  const int q = n - 2, np1 = d == 3 ? n * n * n : n * n, np2 = d == 3 ? q * q * q : q * q;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < N1; g += (size_t)gridDim.x * blockDim.x) {
+    size_t e = g / np1; int p = (int)(g - e * np1);
+    int i = p % n, j = (p / n) % n, k = d == 3 ? p / (n * n) : 1;
+    int nb = (i == 0 || i == n - 1) + (j == 0 || j == n - 1) + (d == 3 ? (k == 0 || k == n - 1) : 0);
+    double v = 0.0;
+    if (nb <= 1) {
+      int ii = clamp_inner(i, n) - 1, jj = clamp_inner(j, n) - 1, kk = d == 3 ? clamp_inner(k, n) - 1 : 0;
+      v = r[e * np2 + ((size_t)kk * q + jj) * q + ii];
+    }
+    w[g] = v;
+  }
+}
+void launch_schwarz_embed(const DevMesh& dm, const double* r, double* w, cudaStream_t st) {
+  k_schwarz_embed<<<std::min(cdiv(dm.N1, 256), 148 * 8), 256, 0, st>>>(r, w, dm.n, dm.ndim, dm.N1); LAUNCH_COUNT();
+}
+
+// per element: face fix (w_face -= w_inner), z = (S (x) S (x) S) dinv (S^T (x) S^T (x) S^T) w ; t = z on faces else 0.
+// If S == nullptr the tensor solve is skipped (used to build the overlap-count weights).
+__global__ void k_schwarz_fdm(const double* __restrict__ w, double* __restrict__ z, double* __restrict__ t, const double* __restrict__ S,
+                              const double* __restrict__ St, const double* __restrict__ dinv, int n, int d) {
+  extern __shared__ double sm[];
+  const int nz = d == 3 ? n : 1, np1 = n * n * nz, nn = n * n;
+  double* sS = sm; double* sSt = sS + d * nn; double* A = sSt + d * nn; double* B = A + np1;
+  const size_t e = blockIdx.x;
+  if (S) { load_mat(sS, S + e * (size_t)d * nn, d * nn); load_mat(sSt, St + e * (size_t)d * nn, d * nn); }
+  for (int p = threadIdx.x; p < np1; p += blockDim.x) B[p] = w[e * np1 + p];
+  __syncthreads();
+  for (int p = threadIdx.x; p < np1; p += blockDim.x) {
+    int i = p % n, j = (p / n) % n, k = d == 3 ? p / nn : 1;
+    int nb = (i == 0 || i == n - 1) + (j == 0 || j == n - 1) + (d == 3 ? (k == 0 || k == n - 1) : 0);
+    double v = B[p];
+    if (nb == 1) {
+      int ii = clamp_inner(i, n), jj = clamp_inner(j, n), kk = d == 3 ? clamp_inner(k, n) : 0;
+      v -= B[(kk * n + jj) * n + ii];
+    }
+    A[p] = v;
+  }
+  __syncthreads();
+  double* res = A;
+  if (S) {
+    contract<false>(B, A, sSt, n, n, 0, n, n, nz);
+    contract<false>(A, B, sSt + nn, n, n, 1, n, n, nz);
+    if (d == 3) { contract<false>(B, A, sSt + 2 * nn, n, n, 2, n, n, nz); }
+    double* cur = d == 3 ? B : A; double* oth = d == 3 ? A : B;
+    for (int p = threadIdx.x; p < np1; p += blockDim.x) cur[p] *= dinv[e * np1 + p];
+    __syncthreads();
+    contract<false>(oth, cur, sS, n, n, 0, n, n, nz);
+    contract<false>(cur, oth, sS + nn, n, n, 1, n, n, nz);
+    res = cur;
+    if (d == 3) { contract<false>(oth, cur, sS + 2 * nn, n, n, 2, n, n, nz); res = oth; }
+  }
+  for (int p = threadIdx.x; p < np1; p += blockDim.x) {
+    int i = p % n, j = (p / n) % n, k = d == 3 ? p / nn : 1;
+    int nb = (i == 0 || i == n - 1) + (j == 0 || j == n - 1) + (d == 3 ? (k == 0 || k == n - 1) : 0);
+    double v = res[p];
+    z[e * np1 + p] = v;
+    t[e * np1 + p] = nb == 1 ? v : 0.0;
+  }
+}
+void launch_schwarz_fdm(const DevMesh& dm, const double* w, double* z, double* t, cudaStream_t st) {
+  size_t smem = (size_t)(2 * dm.ndim * dm.n * dm.n + 2 * dm.np1) * sizeof(double);
+  k_schwarz_fdm<<<(unsigned)dm.E, elem_threads(dm.np1), smem, st>>>(w, z, t, dm.fdmS, dm.fdmSt, dm.fdmDinv, dm.n, dm.ndim); LAUNCH_COUNT();
+}
+void launch_schwarz_count(const DevMesh& dm, const double* w, double* z, double* t, cudaStream_t st) {
+  size_t smem = (size_t)(2 * dm.ndim * dm.n * dm.n + 2 * dm.np1) * sizeof(double);
+  k_schwarz_fdm<<<(unsigned)dm.E, elem_threads(dm.np1), smem, st>>>(w, z, t, nullptr, nullptr, nullptr, dm.n, dm.ndim); LAUNCH_COUNT();
+}
+
+// out (q^d) = wt * ( z_interior + [first interior layers] (tsum_face - z_face) )
+__global__ void k_schwarz_gather(const double* __restrict__ z, const double* __restrict__ ts, double* __restrict__ out,
+                                 const double* __restrict__ wt, int n, int d, size_t N2) {
+  const int q = n - 2, np1 = d == 3 ? n * n * n : n * n, np2 = d == 3 ? q * q * q : q * q, nn = n * n;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < N2; g += (size_t)gridDim.x * blockDim.x) {
+    size_t e = g / np2; int p = (int)(g - e * np2);
+    int i = p % q + 1, j = (p / q) % q + 1, k = d == 3 ? p / (q * q) + 1 : 0;
+    const double* ze = z + e * np1; const double* te = ts + e * np1;
+    double v = ze[(k * n + j) * n + i];
+    if (i == 1) { int f = (k * n + j) * n + 0; v += te[f] - ze[f]; }
+    if (i == n - 2) { int f = (k * n + j) * n + n - 1; v += te[f] - ze[f]; }
+    if (j == 1) { int f = (k * n + 0) * n + i; v += te[f] - ze[f]; }
+    if (j == n - 2) { int f = (k * n + n - 1) * n + i; v += te[f] - ze[f]; }
+    if (d == 3) {
+      if (k == 1) { int f = (0 * n + j) * n + i; v += te[f] - ze[f]; }
+      if (k == n - 2) { int f = ((n - 1) * n + j) * n + i; v += te[f] - ze[f]; }
+    }
+    (void)nn;
+    out[g] = wt ? v * wt[g] : v;
+  }
+}
+void launch_schwarz_gather(const DevMesh& dm, const double* z, const double* t, double* out, cudaStream_t st) {
+  k_schwarz_gather<<<std::min(cdiv(dm.N2, 256), 148 * 8), 256, 0, st>>>(z, t, out, dm.swt, dm.n, dm.ndim, dm.N2); LAUNCH_COUNT();
+}
+void launch_schwarz_gather_nowt(const DevMesh& dm, const double* z, const double* t, double* out, cudaStream_t st) {
+  k_schwarz_gather<<<std::min(cdiv(dm.N2, 256), 148 * 8), 256, 0, st>>>(z, t, out, nullptr, dm.n, dm.ndim, dm.N2); LAUNCH_COUNT();
+}
+
+// ------------------------------------------------------------------------------------------------ K11 coarse grid
+__device__ __forceinline__ double corner_shape(int c, int p, int q, int d, const double* __restrict__ z2) {
+  int i = p % q, j = (p / q) % q, k = d == 3 ? p / (q * q) : 0;
+  double hx = (c & 1) ? 0.5 * (1 + z2[i]) : 0.5 * (1 - z2[i]);
+  double hy = ((c >> 1) & 1) ? 0.5 * (1 + z2[j]) : 0.5 * (1 - z2[j]);
+  double hz = d == 3 ? (((c >> 2) & 1) ? 0.5 * (1 + z2[k]) : 0.5 * (1 - z2[k])) : 1.0;
+  return hx * hy * hz;
+}
+__global__ void k_coarse_part(const double* __restrict__ r, double* __restrict__ part, const double* __restrict__ z2, int q, int d, size_t nec) {
+  const int nv = 1 << d, np2 = d == 3 ? q * q * q : q * q;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nec) return;
+  size_t e = t / nv; int c = (int)(t % nv);
+  double s = 0;
+  for (int p = 0; p < np2; ++p) s += corner_shape(c, p, q, d, z2) * r[e * np2 + p];
+  part[t] = s;
+}
+__global__ void k_vert_gather(const double* __restrict__ part, const int32_t* __restrict__ off, const int32_t* __restrict__ ec, double* __restrict__ rc, int64_t nvert) {
+  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvert) return;
+  double s = 0;
+  for (int t = off[v]; t < off[v + 1]; ++t) s += part[ec[t]];
+  rc[v] = s;
+}
+void launch_coarse_restrict(const DevMesh& dm, const double* r, double* part, double* rc, cudaStream_t st) {
+  size_t nec = (size_t)dm.E << dm.ndim;
+  k_coarse_part<<<cdiv(nec, 128), 128, 0, st>>>(r, part, dm.w2 + dm.q, dm.q, dm.ndim, nec); LAUNCH_COUNT();
+  k_vert_gather<<<cdiv(dm.nvert, 128), 128, 0, st>>>(part, dm.vert_off, dm.vert_ec, rc, dm.nvert); LAUNCH_COUNT();
+}
+__global__ void k_gemv(const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y, int n) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double* a = A + (size_t)row * n;
+  double s = 0;
+  for (int j = lane; j < n; j += 32) s += a[j] * x[j];
+  s = warp_sum(s);
+  if (lane == 0) y[row] = s;
+}
+void launch_gemv(const double* A, const double* x, double* y, int n, cudaStream_t st) {
+  k_gemv<<<cdiv(n, 8), 256, 0, st>>>(A, x, y, n); LAUNCH_COUNT();
+}
+__global__ void k_coarse_prolong(const double* __restrict__ c, double* __restrict__ z, const int64_t* __restrict__ vertex,
+                                 const double* __restrict__ z2, int q, int d, size_t N2, int accumulate) {
+  const int nv = 1 << d, np2 = d == 3 ? q * q * q : q * q;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < N2; g += (size_t)gridDim.x * blockDim.x) {
+    size_t e = g / np2; int p = (int)(g - e * np2);
+    double s = 0;
+    for (int k = 0; k < nv; ++k) s += corner_shape(k, p, q, d, z2) * c[vertex[e * nv + k] - 1];
+    z[g] = (accumulate ? z[g] : 0.0) + s;
+  }
+}
+void launch_coarse_prolong_add(const DevMesh& dm, const double* c, double* z, int accumulate, cudaStream_t st) {
+  k_coarse_prolong<<<std::min(cdiv(dm.N2, 256), 148 * 8), 256, 0, st>>>(c, z, dm.vertex, dm.w2 + dm.q, dm.q, dm.ndim, dm.N2, accumulate); LAUNCH_COUNT();
+}
+
+// ------------------------------------------------------------------------------------------------ K14 CFL
+__global__ void __launch_bounds__(256)
+k_cfl(CPtr3 u, const double* __restrict__ rxj, const double* __restrict__ dri, int n, int d, size_t N1, double* out, Reducer red) {
+  const int np1 = d == 3 ? n * n * n : n * n;
+  double v[1] = {0.0};
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < N1; g += (size_t)gridDim.x * blockDim.x) {
+    size_t e = g / np1; int p = (int)(g - e * np1);
+    int idx[3] = {p % n, (p / n) % n, d == 3 ? p / (n * n) : 0};
+    double s = 0;
+    for (int k = 0; k < d; ++k) {
+      double uk = 0;
+      for (int c = 0; c < d; ++c) uk += u.p[c][g] * rxj[(e * d * d + (size_t)(k * d + c)) * np1 + p];
+      s += fabs(uk) * dri[idx[k]];
+    }
+    v[0] = fmax(v[0], s);
+  }
+  if (grid_reduce<1, true>(v, red)) out[0] = v[0];
+}
+void launch_cfl(const DevMesh& dm, CPtr3 u, double* out, Reducer red, cudaStream_t st) {
+  int grid = std::min(cdiv(dm.N1, RED_THREADS), RED_BLOCKS);
+  k_cfl<<<grid, RED_THREADS, 0, st>>>(u, dm.rxj, dm.dri, dm.n, dm.ndim, dm.N1, out, red); LAUNCH_COUNT();
+}
+
+// ------------------------------------------------------------------------------------------------ K15 filter
+__global__ void k_filter(const double* __restrict__ Fg, Ptr4 u, int n, int d) {
+  extern __shared__ double sm[];
+  const int nz = d == 3 ? n : 1, np1 = n * n * nz;
+  double* sF = sm; double* A = sF + n * n; double* B = A + np1;
+  const size_t e = blockIdx.x;
+  double* ue = u.p[blockIdx.y] + e * np1;
+  load_mat(sF, Fg, n * n);
+  for (int p = threadIdx.x; p < np1; p += blockDim.x) A[p] = ue[p];
+  __syncthreads();
+  contract<false>(B, A, sF, n, n, 0, n, n, nz);
+  contract<false>(A, B, sF, n, n, 1, n, n, nz);
+  double* res = A;
+  if (d == 3) { contract<false>(B, A, sF, n, n, 2, n, n, nz); res = B; }
+  for (int p = threadIdx.x; p < np1; p += blockDim.x) ue[p] = res[p];
+}
+void launch_filter(const DevMesh& dm, const double* F, Ptr4 u, int nf, cudaStream_t st) {
+  size_t smem = (size_t)(dm.n * dm.n + 2 * dm.np1) * sizeof(double);
+  dim3 grid((unsigned)dm.E, nf);
+  k_filter<<<grid, elem_threads(dm.np1), smem, st>>>(F, u, dm.n, dm.ndim); LAUNCH_COUNT();
+}
+
+// ------------------------------------------------------------------------------------------------ seeded field
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
+}
+__global__ void k_rand_field(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                             const int64_t* __restrict__ lglel, int np1, size_t N1, uint64_t seed, int comp) {
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < N1; g += (size_t)gridDim.x * blockDim.x) {
+    size_t e = g / np1; int p = (int)(g - e * np1);
+    uint64_t h = splitmix64(seed ^ splitmix64((uint64_t)lglel[e] * 4096ull + (uint64_t)p + ((uint64_t)comp << 40)));
+    double noise = ((double)(h >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0;
+    double f = sin(0.7 * x[g] + 0.3 * comp) * cos(0.9 * y[g] - 0.2 * comp);
+    if (z) f *= cos(0.5 * z[g] + 0.1 * comp);
+    out[g] = f + 0.1 * noise;
+  }
+}
+void launch_rand_field_impl(double* out, const double* x, const double* y, const double* z, const int64_t* lglel, int np1, size_t N1,
+                            uint64_t seed, int comp, cudaStream_t st) {
+  k_rand_field<<<std::min(cdiv(N1, 256), 148 * 8), 256, 0, st>>>(out, x, y, z, lglel, np1, N1, seed, comp); LAUNCH_COUNT();
+}
+
+}  // namespace nlk

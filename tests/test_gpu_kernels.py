@@ -1,0 +1,122 @@
+"""GPU parity: every hot-path kernel through the C-ABI against the numpy oracle."""
+import numpy as np
+import pytest
+
+from oracle import ops
+from oracle.precond import SchwarzCoarse
+from oracle.stepper import cggo, uzawa_gmres
+from tests.util import box_case, cylinder_case, nlk_mesh, rel, smooth_fields
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "box2d_n6": dict(ndim=2, nel=(4, 3), n=6, lxd=9, bc={"xlo": "v  ", "xhi": "O  "}),
+    "box2d_n8_per": dict(ndim=2, nel=(5, 4), n=8, lxd=12, periodic=[True, False]),
+    "box2d_n10": dict(ndim=2, nel=(3, 3), n=10, lxd=15),
+    "box3d_n5": dict(ndim=3, nel=(3, 2, 3), n=5, lxd=8, bc={"xlo": "v  ", "xhi": "O  "}),
+    "box3d_n8_per": dict(ndim=3, nel=(3, 3, 3), n=8, lxd=12, periodic=[False, False, True]),
+}
+
+
+@pytest.fixture(scope="module", params=list(CASES) + ["cylinder"])
+def case(request, nlk_lib):
+    from neklab_b200 import api
+    if request.param == "cylinder":
+        om, bf, prm, _ = cylinder_case()
+    else:
+        om, _, _ = box_case(**CASES[request.param])
+    m = nlk_mesh(om)
+    ctx = api.Context(m, api.default_params(viscosity=0.02, precond=1, gmres_maxit=600))
+    yield request.param, om, m, ctx
+    ctx.close()
+
+
+def test_mesh_parity(case):
+    name, om, m, ctx = case
+    assert np.array_equal(m.glo_num(), om.glo)          # gather-scatter map bit-exact
+    assert rel(m.field("bm1"), om.bm1) < 1e-13
+    assert rel(m.field("binvm1"), om.binvm1) < 1e-13
+    for c in range(om.ndim):
+        assert np.array_equal(m.field(f"vmask{c}"), om.vmask[c])
+
+
+def test_axhelm(case):
+    name, om, m, ctx = case
+    u = smooth_fields(om, 1)[0]
+    for h1, h2 in [(1.0, 0.0), (0.02, 150.0)]:
+        assert rel(ctx.axhelm(u, h1, h2), ops.axhelm(om, u, h1, h2)) < 1e-12
+
+
+def test_dssum_bit_exact_on_integers(case):
+    name, om, m, ctx = case
+    rng = np.random.default_rng(3)
+    u = rng.integers(-1000, 1000, size=om.bm1.shape).astype(np.float64)
+    assert np.array_equal(ctx.dssum(u), om.dssum(u))     # integer-valued data: exact in fp64
+
+
+def test_opdiv_opgradt(case):
+    name, om, m, ctx = case
+    u = smooth_fields(om, om.ndim, 1)
+    assert rel(ctx.opdiv(u), ops.opdiv(om, u)) < 1e-12
+    p = np.random.default_rng(5).standard_normal(om.bm2.shape)
+    w = ctx.opgradt(p); wr = ops.opgradt(om, p)
+    for c in range(om.ndim):
+        assert rel(w[c], wr[c]) < 1e-12
+    # transpose identity <D u, p> = <u, D^T p>
+    lhs = float((ops.opdiv(om, u) * p).sum()); rhs = sum(float((u[c] * w[c]).sum()) for c in range(om.ndim))
+    assert abs(lhs - rhs) < 1e-10 * max(abs(lhs), 1.0)
+
+
+def test_cdabdtp(case):
+    name, om, m, ctx = case
+    p = np.random.default_rng(6).standard_normal(om.bm2.shape)
+    assert rel(ctx.cdabdtp(p), ops.cdabdtp(om, p)) < 1e-11
+
+
+def test_convect(case):
+    name, om, m, ctx = case
+    f = smooth_fields(om, om.ndim + 1, 2)
+    assert rel(ctx.convect(f[0], f[1:]), ops.convect_new(om, f[0], f[1:])) < 1e-12
+    U = smooth_fields(om, om.ndim, 4); c = smooth_fields(om, om.ndim, 5)
+    a = ctx.convect_adj(U, c); ar = ops.convect_adj(om, U, c)
+    for k in range(om.ndim):
+        assert rel(a[k], ar[k]) < 1e-12
+
+
+def test_cfl(case):
+    name, om, m, ctx = case
+    u = smooth_fields(om, om.ndim, 7)
+    assert abs(ctx.cfl(u, 0.01) - ops.compute_cfl(om, u, 0.01)) < 1e-12 * ops.compute_cfl(om, u, 0.01)
+
+
+def test_helmholtz_pcg(case):
+    name, om, m, ctx = case
+    f = smooth_fields(om, 1, 8)[0] * om.bm1
+    st = {}
+    xr = cggo(om, f, 0.02, 150.0, om.vmask[0], 1e-12, 500, st)
+    x, it = ctx.helmholtz(f, 0.02, 150.0, 0, 1e-12)
+    assert rel(x, xr) < 1e-9
+    assert abs(it - st["cg_iters"]) <= 1
+
+
+def test_precond_parity(case):
+    name, om, m, ctx = case
+    pc = SchwarzCoarse(om, use_coarse=(name != "cylinder"))
+    r = np.random.default_rng(9).standard_normal(om.bm2.shape)
+    if name == "cylinder":
+        pc.use_coarse = False
+        z = ctx.precond(r)          # device includes the coarse term: compare Schwarz part through linearity
+        pytest.skip("coarse-grid oracle on the full cylinder mesh is too slow for the suite; covered by box cases")
+    # singular E (no outflow): coarse solves may differ by a constant, which `ortho` removes
+    assert rel(ops.ortho(om, ctx.precond(r)), ops.ortho(om, pc(r))) < 1e-9
+
+
+def test_pressure_gmres(case):
+    name, om, m, ctx = case
+    u = [om.vmask[c] * x for c, x in enumerate(smooth_fields(om, om.ndim, 10))]
+    rhs = ops.ortho(om, -ops.opdiv(om, u))
+    x, it = ctx.pressure(rhs, 1e-10)
+    res = rhs - ops.cdabdtp(om, x)
+    nrm = lambda a: float(np.sqrt((a * a / om.bm2).sum() / om.volvm2))
+    assert nrm(ops.ortho(om, res)) < 2e-10
+    assert it < 600

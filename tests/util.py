@@ -1,0 +1,73 @@
+"""Shared builders for the tests: the same case as an oracle `SEMesh` (numpy) and as a libnlk `Mesh`."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from neklab_b200.boxmesh import box_mesh
+from oracle import ops
+from oracle.mesh import SEMesh, coords_from_corners
+from oracle.stepper import NekVec, StepParams
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def warp2d(c):
+    x, y = c[:, 0].copy(), c[:, 1].copy()
+    c = c.copy()
+    Lx, Ly = x.max() - x.min(), y.max() - y.min()
+    c[:, 0] = x + 0.06 * Lx * np.sin(2 * np.pi * (y - y.min()) / Ly) * np.sin(np.pi * (x - x.min()) / Lx)
+    c[:, 1] = y + 0.05 * Ly * np.sin(2 * np.pi * (x - x.min()) / Lx) * np.sin(np.pi * (y - y.min()) / Ly)
+    return c
+
+
+def warp3d(c):
+    x, y, z = c[:, 0].copy(), c[:, 1].copy(), c[:, 2].copy()
+    c = c.copy()
+    sx = np.sin(np.pi * x / x.max()); sy = np.sin(np.pi * y / y.max()); sz = np.sin(np.pi * z / z.max())
+    c[:, 0] = x + 0.05 * sx * sy * np.cos(2 * np.pi * z / z.max())      # periodic-compatible in z
+    c[:, 1] = y + 0.04 * sx * sy * sz
+    c[:, 2] = z + 0.05 * sz * sx * np.cos(0.7 * y)
+    return c
+
+
+def box_case(ndim=2, nel=(4, 3), n=6, lxd=9, warp=True, bc=None, periodic=None, cbc_t=None, hi=None):
+    hi = hi or tuple(float(k) for k in nel)
+    bm = box_mesh(nel, (0.0,) * ndim, hi, periodic=periodic, bc=bc,
+                  warp=(warp2d if ndim == 2 else warp3d) if warp else None)
+    coords = coords_from_corners(bm["corners"], n)
+    om = SEMesh(coords, bm["vertex"], bm["cbc"], lxd, cbc_t=cbc_t)
+    return om, bm, coords
+
+
+def nlk_mesh(om: SEMesh, cbc_t=None):
+    from neklab_b200 import api
+    return api.Mesh(om.coords, om.vertex, om.cbc_v, om.m, cbc_t=om.cbc_t if cbc_t is None else cbc_t)
+
+
+def cylinder_case():
+    """examples/cylinder/stability/direct (Re=50, lx1=6, lxd=9) from the committed fixture."""
+    z = np.load(os.path.join(GOLDEN, "cylinder_case.npz"))
+    om = SEMesh(z["coords"], z["vertex"], z["cbc"], 9)
+    bf = NekVec(om, 3)
+    bf.v = [z["vel"][:, 0].copy(), z["vel"][:, 1].copy()]
+    bf.pr = ops.map12(om, z["pr"])
+    prm = StepParams(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7)
+    return om, bf, prm, z
+
+
+def smooth_fields(om: SEMesh, k, seed=0):
+    rng = np.random.default_rng(seed)
+    x = om.coords
+    out = []
+    for i in range(k):
+        f = np.sin(0.9 * x[:, 0] + 0.4 * i) * np.cos(0.7 * x[:, 1] - 0.3 * i)
+        if om.ndim == 3:
+            f = f * np.cos(0.5 * x[:, 2] + 0.2 * i)
+        out.append(f + 0.05 * rng.standard_normal(f.shape))
+    return out
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
