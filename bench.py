@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- exptA matvec throughput on B200 (BASELINE.json metric: exptA matvec/s & GDOF.steps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload cylinder|synth3d]
+
+Workloads
+  cylinder : examples/cylinder/stability/direct of the reference (Re=50, 1996 el, lx1=6, lxd=9, bdf3, tau=1,
+             100+2 time steps per matvec).  One bench "step" = one exptA matvec.           [default, N=1]
+  synth3d  : the 2-D cylinder mesh extruded periodically in z (lx1=8, lxd=12), element-partitioned over the ranks
+             (weak scaling: --layers z-layers PER GPU).  One bench "step" = one perturbation time step.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events on the library's stream, max over ranks) with
+inputs resident in HBM; `e2e` goes through the public C-ABI with host buffers (H2D of the input vector and D2H of the
+result inside the timed region).  `--impl reference` times the CPU restatement oracle (the Fortran/MPI reference
+cannot be built in this image: no Fortran compiler, no MPI) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu=0):
+        self.gpu = gpu; self.rows = []; self.p = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- workloads
+def cylinder_inputs():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cylinder_case.npz"))
+    return dict(coords=z["coords"], vertex=z["vertex"], cbc=z["cbc"], vel=z["vel"], pr=z["pr"], pid=z["pid"])
+
+
+def extrude(case, n, layers_total, lz_per_layer=0.5):
+    """Extrude the 2-D cylinder mesh (bilinear re-interpolation to lx1=n) into `layers_total` periodic z-layers."""
+    from oracle.sem import gll, interp_matrix      # 1-D nodes only (host-side input generation, not the measured path)
+    c2 = case["coords"]; E2 = c2.shape[0]; n0 = c2.shape[-1]
+    z0, _ = gll(n0); z1, _ = gll(n)
+    I = interp_matrix(z1, z0)
+    up = lambda a: np.einsum("qj,pi,e...ji->e...qp", I, I, a)
+    xy = up(c2[:, :, 0]); vel = up(case["vel"][:, :, 0])
+    L = layers_total
+    coords = np.zeros((E2 * L, 3, n, n, n)); U = np.zeros((E2 * L, 3, n, n, n))
+    zz = 0.5 * (z1 + 1.0) * lz_per_layer
+    nv2 = int(case["vertex"].max())
+    vertex = np.zeros((E2 * L, 8), dtype=np.int64)
+    cbc = np.full((E2 * L, 6), "E  ", dtype="U3")
+    for l in range(L):
+        sl = slice(l * E2, (l + 1) * E2)
+        coords[sl, 0] = xy[:, 0][:, None]; coords[sl, 1] = xy[:, 1][:, None]
+        coords[sl, 2] = (l * lz_per_layer + zz)[None, :, None, None]
+        U[sl, 0] = vel[:, 0][:, None]; U[sl, 1] = vel[:, 1][:, None]
+        vertex[sl, :4] = case["vertex"] + l * nv2
+        vertex[sl, 4:] = case["vertex"] + ((l + 1) % L) * nv2
+        cbc[sl, :4] = case["cbc"]; cbc[sl, 4:] = "P  "
+    return coords, U, vertex, cbc
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None, "cylinder", "synth3d"])
+    ap.add_argument("--layers", type=int, default=4, help="synth3d: z-layers per GPU (1996 elements each)")
+    ap.add_argument("--cpu-steps", type=int, default=6, help="time steps in the CPU-baseline sample")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = a.workload or ("cylinder" if world == 1 else "synth3d")
+    steps = a.steps if a.steps is not None else (5 if workload == "cylinder" else 3)
+    if a.impl == "reference":
+        if rank == 0:
+            print(json.dumps(reference_arm(workload, steps, a.warmup, a)), flush=True)
+        return
+    out = native_arm(workload, steps, a.warmup, a, rank, world, local)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- CPU baseline (oracle)
+def cpu_sample(nsteps_sample):
+    """Time `nsteps_sample` perturbation time steps of the cylinder config with the numpy oracle (same algorithm:
+    Jacobi-PCG + Schwarz/coarse FGMRES).  Returns (seconds per time step, description)."""
+    from oracle.precond import SchwarzCoarse
+    from oracle.stepper import PertStepper, seeded_field
+    from tests.util import cylinder_case
+    om, bf, prm, _ = cylinder_case()
+    prm.gmres_maxit = 100
+    pc = SchwarzCoarse(om)
+    st = PertStepper(om, prm, precond=pc)
+    st.U = [x.copy() for x in bf.v]
+    st.setup(1.0, 0.5, False)
+    x0 = seeded_field(om, 12345)
+    st.set_state(x0.v, x0.pr, x0.theta); st.reset_history()
+    st.advance(1)                                   # warm caches / BDF1 step not timed
+    t0 = time.perf_counter()
+    for i in range(2, 2 + nsteps_sample):
+        st.advance(i)
+    dt = (time.perf_counter() - t0) / nsteps_sample
+    return dt, st.nsteps, om, st.stats
+
+
+def reference_arm(workload, steps, warmup, a):
+    cores = os.cpu_count() or 1
+    sec_step, nsteps, om, stats = cpu_sample(max(2, a.cpu_steps))
+    n_ts = nsteps + 2
+    matvec_s = 1.0 / (sec_step * n_ts)
+    unit = "matvec/s"
+    val = matvec_s
+    sample = f"{max(2, a.cpu_steps)} perturbation time steps of the cylinder Re=50 config (of {n_ts} per matvec), numpy oracle, extrapolated"
+    if workload == "synth3d":
+        unit = "GDOF*steps/s"; val = om.bm1.size * 1e-9 / sec_step
+        sample += " (2-D cylinder slice; 3-D oracle not run)"
+    return {"metric": "exptA matvec/s" if workload == "cylinder" else "GDOF*steps/s", "value": val, "unit": unit, "n_gpus": 0,
+            "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / val if workload == "cylinder" else sec_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "impl": "reference", "config": {"workload": workload + ("_re50_exptA_matvec" if workload == "cylinder" else "")},
+            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU restatement oracle (numpy); the Fortran/MPI reference cannot be built in this image"}
+
+
+# ----------------------------------------------------------------------------------------------- native arm
+def native_arm(workload, steps, warmup, a, rank, world, local):
+    from neklab_b200 import api, build
+    if rank == 0:
+        build.build()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        torch.cuda.set_device(local)
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_
+        dist.barrier()
+    peak, peak_src = load_peaks()
+    case = cylinder_inputs()
+    nccl_id = None
+    if workload == "cylinder":
+        gllnid = None
+        if world > 1:
+            gllnid = api.partition(case["pid"], world)
+        sel = slice(None) if gllnid is None else np.where(gllnid == rank)[0]
+        mesh = api.Mesh(case["coords"][sel], case["vertex"], case["cbc"], 9, gllnid=gllnid, rank=rank, nranks=world)
+        prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7)
+        tau = 1.0
+        vel = case["vel"][sel][:, :, 0]
+        U = [vel[:, 0][:, None], vel[:, 1][:, None]]
+    else:
+        L = a.layers * world
+        coords, Uall, vertex, cbc = extrude(case, 8, L)
+        E2 = case["coords"].shape[0]
+        gllnid = (np.arange(E2 * L) // (E2 * a.layers)).astype(np.int32) if world > 1 else None      # z-slabs
+        sel = slice(None) if gllnid is None else np.where(gllnid == rank)[0]
+        mesh = api.Mesh(coords[sel], vertex, cbc, 12, gllnid=gllnid, rank=rank, nranks=world)
+        prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7)
+        tau = None
+        U = [Uall[sel, 0], Uall[sel, 1], Uall[sel, 2]]
+    if world > 1:
+        import torch
+        buf = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(buf, src=0)
+        nccl_id = buf[0]
+    ctx = api.Context(mesh, prm, device=local, nccl_id=nccl_id)
+    bf = ctx.vec(); bf.upload(U)
+    x = ctx.vec(); x.rand(ifnorm=True, seed=12345)
+    y = ctx.vec()
+    npts = mesh.nel * mesh.shape1[1] * mesh.shape1[2] * mesh.shape1[3]
+    sampler = ClockSampler(local)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    if workload == "cylinder":
+        A = api.exptA_linop(ctx, tau, bf)
+        A.init()
+        for _ in range(warmup):
+            A.matvec(x, y)
+        barrier(); sampler.start()
+        ms = 0.0; launches = 0; cg = gm = ts = 0
+        for _ in range(steps):
+            A.matvec(x, y)
+            s = A.stats(); ms += s["ms_total"]; launches += s["launches"]; cg += s["cg_iters"]; gm += s["gmres_iters"]; ts += s["steps"]
+        barrier(); clocks = sampler.stop()
+        ms_step = ms / steps
+        # e2e: host buffers in, host buffers out, through the public API
+        hv, hp, _ = x.download()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            x.upload(hv, hp)
+            A.matvec(x, y)
+            ov, op, _ = y.download()
+        ctx.sync()
+        e2e_s = (time.perf_counter() - t0) / steps
+        vec_bytes = sum(v.nbytes for v in hv) + hp.nbytes
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms_step, e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_step, e2e_s = float(t[0]), float(t[1])
+        value = 1e3 / ms_step; unit = "matvec/s"; metric = "exptA matvec/s"
+        e2e = {"value": 1.0 / e2e_s, "unit": unit, "h2d_bytes_per_step": int(vec_bytes), "d2h_bytes_per_step": int(vec_bytes)}
+        npts_global = case["coords"].shape[0] * 36
+        extra = {"gdof_steps_per_s": npts_global * 1e-9 * (ts / steps) / (ms_step * 1e-3), "time_steps_per_matvec": ts // steps,
+                 "cg_iters_per_step": cg / max(ts, 1), "gmres_iters_per_step": gm / max(ts, 1), "launches_per_time_step": launches / max(ts, 1)}
+        cfg = {"workload": "cylinder_re50_exptA_matvec", "elements": int(case["coords"].shape[0]), "lx1": 6, "lxd": 9, "timestepper": "bdf3",
+               "tau": 1.0, "partition": ("single" if world == 1 else f".ma2 power-of-two rule over {world} ranks"),
+               "l2": "working set (~20 MB) is L2-resident by construction (reference config size)"}
+    else:
+        import ctypes as C
+        L_ = api.lib()
+        # one bench step = one perturbation time step (the body of the exptA loop); state stays in HBM
+        A = api.exptA_linop(ctx, 1.0, bf)
+        s0 = A.init()
+        # drive time steps through a short-horizon matvec: tau = k*dt gives exactly k steps (+2 rst steps)
+        dt = s0["dt"]
+        L_.nlk_exptA_set_tau(A.h, C.c_double(dt * max(1, warmup)))
+        A.matvec(x, y)
+        L_.nlk_exptA_set_tau(A.h, C.c_double(dt * steps))
+        barrier(); sampler.start()
+        A.matvec(x, y)
+        barrier(); clocks = sampler.stop()
+        s = A.stats()
+        ts = s["steps"]; ms_step = s["ms_total"] / ts
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms_step], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_step = float(t[0])
+        npts_global = npts * world
+        value = npts_global * 1e-9 / (ms_step * 1e-3); unit = "GDOF*steps/s"; metric = "GDOF*steps/s"
+        hv, hp, _ = x.download()
+        t0 = time.perf_counter(); x.upload(hv, hp); A.matvec(x, y); ov, op, _ = y.download(); ctx.sync()
+        e2e_s = (time.perf_counter() - t0) / ts
+        vec_bytes = sum(v.nbytes for v in hv) + hp.nbytes
+        e2e = {"value": npts_global * 1e-9 / e2e_s, "unit": unit, "h2d_bytes_per_step": int(vec_bytes // ts), "d2h_bytes_per_step": int(vec_bytes // ts)}
+        launches = s["launches"]
+        extra = {"time_steps_timed": int(ts), "cg_iters_per_step": s["cg_iters"] / ts, "gmres_iters_per_step": s["gmres_iters"] / ts,
+                 "launches_per_time_step": launches / ts, "dt": dt}
+        cfg = {"workload": "synth3d_extruded_cylinder_time_step", "elements": int(mesh.nel * world), "lx1": 8, "lxd": 12, "layers_per_gpu": a.layers,
+               "partition": "z-slabs of whole 2-D layers", "l2": "inputs larger than L2 (%.0f MB of state+geometry per GPU)" % (npts * 8 * 40 / 1e6)}
+    # roofline of the dominant kernel (K1 axhelm) at this problem size, CUDA events on the library stream
+    ms_ax, bytes_ax = ctx.bench_kernel(0, 200)
+    roof = {"kernel": "k_axhelm (K1, Helmholtz apply inside Jacobi-PCG)", "bound": "hbm", "achieved": bytes_ax / (ms_ax * 1e-3) / 1e9,
+            "peak": peak, "unit": "GB/s", "frac": bytes_ax / (ms_ax * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "us_per_launch": ms_ax * 1e3, "algorithmic_bytes_per_launch": bytes_ax}
+    other = {}
+    for name, which in (("dssum", 1), ("cdabdtp", 2), ("convect", 3), ("precond", 4), ("vec_dot", 5)):
+        m_, b_ = ctx.bench_kernel(which, 50)
+        other[name] = {"us": m_ * 1e3, "GBps": b_ / (m_ * 1e-3) / 1e9}
+    out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
+           "higher_is_better": True, "scaling": "weak" if workload == "synth3d" else "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+           "kernels": other, **extra}
+    if world == 1 and rank == 0 and os.environ.get("NLK_BENCH_NO_CPU") != "1":
+        try:
+            sec_step, nsteps, om, stats = cpu_sample(max(2, a.cpu_steps))
+            if workload == "cylinder":
+                v = 1.0 / (sec_step * (nsteps + 2)); u = "matvec/s"
+            else:
+                v = om.bm1.size * 1e-9 / sec_step; u = "GDOF*steps/s"
+            out["cpu_baseline"] = {"value": v, "unit": u, "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": f"{max(2, a.cpu_steps)} time steps of the cylinder Re=50 config with the numpy oracle (BLAS threads <= cores), extrapolated to the unit"}
+        except Exception as e:  # the baseline is a reported number, never the product path
+            out["cpu_baseline"] = {"value": None, "unit": unit, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {e}"}
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return out
+
+
+if __name__ == "__main__":
+    main()

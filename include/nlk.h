@@ -94,6 +94,10 @@ typedef struct {
   int32_t precond;         /* 0 = mass-scaled identity, 1 = Schwarz + coarse (semg_xxt analogue) */
   int32_t pr_proj;         /* residualProj: size of the pressure projection space (0 = off, Nek mxprev=20) */
   double cfl_limit;        /* 0.5 for the linear solver (src/linops/exponential_propagator.f90:12) */
+  int32_t rst_mode;        /* 0 (default) = restart-field arithmetic exactly as written in src/vectors/real_vectors.f90:186-200
+                              (rst slots receive alpha * the CURRENT fields of the other vector);
+                              1 = consistent combination of the rst fields; 2 = matvec ignores input rst fields.
+                              1/2 are NOT the reference behaviour; they exist to document its effect */
 } nlk_params;
 
 int nlk_params_default(nlk_params* p);

@@ -195,7 +195,7 @@ static int ctx_setup(nlk_ctx* c) {
     c->have_schwarz = true;
     // coarse operator A0 = R0 E R0^T, column by column on the device; dense inverse on the host
     const int64_t nvt = hm.nvert;
-    if (nvt <= 12000 && c->prm.precond != 2) {
+    if (nvt <= 5000 && c->prm.precond != 2) {
       if (dev_alloc(c, &c->crs_part, (size_t)hm.E << d) || dev_alloc(c, &c->crs_r, nvt) || dev_alloc(c, &c->crs_y, nvt)) return 1;
       double* dA0 = nullptr; if (dev_alloc(c, &dA0, (size_t)nvt * nvt)) return 1;
       for (int64_t v = 0; v < nvt; ++v) {
@@ -233,7 +233,7 @@ int nlk_params_default(nlk_params* p) {
   std::memset(p, 0, sizeof(*p));
   p->viscosity = 1.0; p->density = 1.0; p->torder = 3; p->vtol = 1e-9; p->ptol = 1e-7; p->ifheat = 0; p->conductivity = 1.0; p->rhocp = 1.0;
   p->ttol = 1e-9; p->filter_weight = 0.0; p->filter_cutoff = 1.0; p->cg_maxit = 1000; p->gmres_maxit = 100; p->lgmres = 30; p->precond = 1;
-  p->pr_proj = 0; p->cfl_limit = 0.5;
+  p->pr_proj = 0; p->cfl_limit = 0.5; p->rst_mode = 0;
   return 0;
 }
 
@@ -369,7 +369,14 @@ int nlk_vec_axpby(double alpha, const nlk_vec* x, double beta, nlk_vec* self) {
     if (c->prm.ifheat) launch_lin(t, dm.N1, beta, t, alpha, x->theta, 0, nullptr, 0, nullptr, nullptr, c->st);
   };
   ax(self->v, self->pr, self->theta);
-  for (int s = 0; s < self->nrst; ++s) ax(self->rv[s], self->rpr[s], self->rth[s]);
+  const int mode = c->prm.rst_mode;
+  for (int s = 0; s < self->nrst; ++s) {
+    if (mode == 1 && x->nrst > s) {      // experimental: consistent rst combination (NOT the reference behaviour)
+      for (int k = 0; k < dm.ndim; ++k) launch_lin(self->rv[s][k], dm.N1, beta, self->rv[s][k], alpha, x->rv[s][k], 0, nullptr, 0, nullptr, nullptr, c->st);
+      launch_lin(self->rpr[s], dm.N2, beta, self->rpr[s], alpha, x->rpr[s], 0, nullptr, 0, nullptr, nullptr, c->st);
+      if (c->prm.ifheat) launch_lin(self->rth[s], dm.N1, beta, self->rth[s], alpha, x->rth[s], 0, nullptr, 0, nullptr, nullptr, c->st);
+    } else ax(self->rv[s], self->rpr[s], self->rth[s]);
+  }
   return 0;
 }
 int nlk_vec_dot(const nlk_vec* a, const nlk_vec* b, double* out) {
@@ -476,7 +483,7 @@ int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose) {
   if (reset_history_pub(c)) return 1;
   for (int istep = 1; istep <= c->nsteps; ++istep) {
     if (step_advance(c, istep)) return 1;
-    if (istep <= nrst && in->nrst > 0) {
+    if (istep <= nrst && in->nrst > 0 && c->prm.rst_mode != 2) {
       if (istep > in->nrst) { set_error("exptA: input vector has fewer rst fields than the temporal order needs"); return 1; }
       if (state_from_vec(c, in->rv[istep - 1], in->rpr[istep - 1], in->rth[istep - 1])) return 1;
     }

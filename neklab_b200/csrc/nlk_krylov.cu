@@ -85,11 +85,16 @@ static int basis_innerprod(nlk_ctx* c, nlk_vec* const* X, int k, const nlk_vec* 
   return 0;
 }
 
-static void axpy_field(nlk_ctx* c, double* y, nlk_vec* const* X, int k, const double* coef, size_t n, int which /*0..2 vel, 3 pr, 4 theta*/) {
+static void axpy_field(nlk_ctx* c, double* y, nlk_vec* const* X, int k, const double* coef, size_t n, int which /*0..2 vel, 3 pr, 4 theta*/, int slot = -1) {
   int grid = std::min((int)((n + 255) / 256), 148 * 8);
   for (int k0 = 0; k0 < k; k0 += KB) {
     AxpyPtrs P{}; int nb = std::min(KB, k - k0);
-    for (int j = 0; j < nb; ++j) { const nlk_vec* x = X[k0 + j]; P.x[j] = which < 3 ? x->v[which] : (which == 3 ? x->pr : x->theta); P.c[j] = coef[k0 + j]; }
+    for (int j = 0; j < nb; ++j) {
+      const nlk_vec* x = X[k0 + j];
+      if (slot >= 0 && x->nrst > slot) P.x[j] = which < 3 ? x->rv[slot][which] : (which == 3 ? x->rpr[slot] : x->rth[slot]);
+      else P.x[j] = which < 3 ? x->v[which] : (which == 3 ? x->pr : x->theta);
+      P.c[j] = coef[k0 + j];
+    }
     k_basis_axpy<<<grid, 256, 0, c->st>>>(y, P, nb, n); ++g_launches;
   }
 }
@@ -101,10 +106,11 @@ static int basis_axpy(nlk_ctx* c, nlk_vec* y, nlk_vec* const* X, int k, const do
   for (int f = 0; f < dm.ndim; ++f) axpy_field(c, y->v[f], X, k, coef, dm.N1, f);
   axpy_field(c, y->pr, X, k, coef, dm.N2, 3);
   if (c->prm.ifheat) axpy_field(c, y->theta, X, k, coef, dm.N1, 4);
+  const int sl = c->prm.rst_mode == 1 ? 1 : 0;    // rst_mode 1 (non-reference): combine the X's rst fields instead
   for (int s = 0; s < y->nrst; ++s) {
-    for (int f = 0; f < dm.ndim; ++f) axpy_field(c, y->rv[s][f], X, k, coef, dm.N1, f);
-    axpy_field(c, y->rpr[s], X, k, coef, dm.N2, 3);
-    if (c->prm.ifheat) axpy_field(c, y->rth[s], X, k, coef, dm.N1, 4);
+    for (int f = 0; f < dm.ndim; ++f) axpy_field(c, y->rv[s][f], X, k, coef, dm.N1, f, sl ? s : -1);
+    axpy_field(c, y->rpr[s], X, k, coef, dm.N2, 3, sl ? s : -1);
+    if (c->prm.ifheat) axpy_field(c, y->rth[s], X, k, coef, dm.N1, 4, sl ? s : -1);
   }
   return 0;
 }
