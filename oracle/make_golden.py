@@ -19,7 +19,8 @@ import numpy as np
 def cylinder_eig(out="tests/golden/cylinder_eig_oracle.json", kdim=128, nev=2, rst_quirk=True):
     from .cases import cylinder
     from .krylov import eigs, RTOL_DP
-    from .stepper import ExptA, PertStepper, seeded_field
+    from .stepper import ExptA, NekVec, PertStepper, seeded_field
+    NekVec.RST_MODE = 0 if rst_quirk else 1
     mesh, bf, prm, _ = cylinder()
     prm.pressure_solver = "direct"; prm.helm_solver = "direct"
     st = PertStepper(mesh, prm)
@@ -45,6 +46,10 @@ def cylinder_eig(out="tests/golden/cylinder_eig_oracle.json", kdim=128, nev=2, r
     with open(out, "w") as f:
         json.dump(rec, f, indent=1)
     print("wrote", out, "modulus", rec["modulus"][:2])
+
+
+def cylinder_eig_consistent():
+    cylinder_eig(out="tests/golden/cylinder_eig_oracle_consistent.json", rst_quirk=False)
 
 
 if __name__ == "__main__":

@@ -449,7 +449,13 @@ class PertStepper:
 
 # --------------------------------------------------------------------------- nek_dvector
 class NekVec:
-    """`nek_dvector` semantics (src/vectors/neklab_vectors.f90:26-50, real_vectors.f90)."""
+    """`nek_dvector` semantics (src/vectors/neklab_vectors.f90:26-50, real_vectors.f90).
+
+    RST_MODE 0 (default) reproduces `nek_daxpby` as written (rst slots += alpha * vec's CURRENT fields,
+    real_vectors.f90:186-200); RST_MODE 1 is the consistent variant (rst slots += alpha * vec's rst fields),
+    kept only to document the effect on the golden eigenvalue.
+    """
+    RST_MODE = 0
 
     def __init__(self, mesh: SEMesh, torder: int = 3, ifheat: bool = False):
         self.mesh, self.torder, self.ifheat = mesh, torder, ifheat
@@ -502,11 +508,15 @@ class NekVec:
             self.theta += alpha * vec.theta
         for i in range(self.nrst):                 # quirk :186-200 -- adds vec's CURRENT fields
             rv, rp, rt = self._rst_slot(i)
+            if NekVec.RST_MODE == 1 and vec.nrst > i:
+                sv, sp, st_ = vec.rst[i]
+            else:
+                sv, sp, st_ = vec.v, vec.pr, vec.theta
             for c in range(len(self.v)):
-                rv[c] += alpha * vec.v[c]
-            rp += alpha * vec.pr
+                rv[c] += alpha * sv[c]
+            rp += alpha * sp
             if self.ifheat:
-                rt += alpha * vec.theta
+                rt += alpha * st_
 
     def dot(self, vec: "NekVec") -> float:         # :208-233  bm1-weighted, pressure excluded
         B = self.mesh.bm1
