@@ -191,7 +191,7 @@ def native_arm(workload, steps, warmup, a, rank, world, local):
             gllnid = api.partition(case["pid"], world)
         sel = slice(None) if gllnid is None else np.where(gllnid == rank)[0]
         mesh = api.Mesh(case["coords"][sel], case["vertex"], case["cbc"], 9, gllnid=gllnid, rank=rank, nranks=world)
-        prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7)
+        prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7, pr_proj=20)   # 1cyl.par: residualProj = yes (mxprev = 20)
         tau = 1.0
         vel = case["vel"][sel][:, :, 0]
         U = [vel[:, 0][:, None], vel[:, 1][:, None]]
@@ -202,7 +202,7 @@ def native_arm(workload, steps, warmup, a, rank, world, local):
         gllnid = (np.arange(E2 * L) // (E2 * a.layers)).astype(np.int32) if world > 1 else None      # z-slabs
         sel = slice(None) if gllnid is None else np.where(gllnid == rank)[0]
         mesh = api.Mesh(coords[sel], vertex, cbc, 12, gllnid=gllnid, rank=rank, nranks=world)
-        prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7)
+        prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7, pr_proj=20)
         tau = None
         U = [Uall[sel, 0], Uall[sel, 1], Uall[sel, 2]]
     if world > 1:

@@ -29,12 +29,13 @@ def main():
     ap.add_argument("--cfl", type=float, default=0.5)
     ap.add_argument("--maxit", type=int, default=100)
     ap.add_argument("--rst-mode", type=int, default=0)
+    ap.add_argument("--proj", type=int, default=20)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     build.build()
     z = load_case()
     mesh = api.Mesh(z["coords"], z["vertex"], z["cbc"], 9)
-    prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=a.vtol, ptol=a.ptol, gmres_maxit=a.maxit, cfl_limit=a.cfl, rst_mode=a.rst_mode)
+    prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=a.vtol, ptol=a.ptol, gmres_maxit=a.maxit, cfl_limit=a.cfl, rst_mode=a.rst_mode, pr_proj=a.proj)
     t0 = time.time()
     ctx = api.Context(mesh, prm)
     print("setup %.2fs" % (time.time() - t0), flush=True)

@@ -99,6 +99,7 @@ static int ctx_setup(nlk_ctx* c) {
   for (int k = 0; k < 5; ++k) if (dev_alloc(c, &c->pw[k], N2)) return 1;
   if (dev_alloc(c, &c->gm_V, (size_t)(c->prm.lgmres + 1) * N2) || dev_alloc(c, &c->gm_Z, (size_t)c->prm.lgmres * N2)) return 1;
   if (dev_alloc(c, &c->sw_w, N1) || dev_alloc(c, &c->sw_z, N1) || dev_alloc(c, &c->sw_t, N1)) return 1;
+  if (c->prm.pr_proj > 0) { if (dev_alloc(c, &c->proj_X, (size_t)c->prm.pr_proj * N2) || dev_alloc(c, &c->proj_EX, (size_t)c->prm.pr_proj * N2) || dev_alloc(c, &c->proj_w, N2) || dev_alloc(c, &c->proj_xbar, N2)) return 1; }
   // ---- device-side setup: global volumes, binvm1, vmult, Jacobi diagonals
   {
     double vols[3] = {hm.volvm1, hm.volvm2, (double)N2};
@@ -186,7 +187,7 @@ static int ctx_setup(nlk_ctx* c) {
     if (dev_upload(c, &dm.fdmS, S) || dev_upload(c, &dm.fdmSt, St) || dev_upload(c, &dm.fdmDinv, dinv)) return 1;
     // overlap-count weights
     if (dev_alloc(c, &dm.swt, N2)) return 1;
-    launch_schwarz_embed(dm, c->ones2, c->sw_w, c->st);
+    launch_schwarz_embed(dm, c->ones2, nullptr, c->sw_w, c->st);
     if (ctx_gs(c, Ptr3{{c->sw_w, nullptr, nullptr}}, 1)) return 1;
     launch_schwarz_count(dm, c->sw_w, c->sw_z, c->sw_t, c->st);
     if (ctx_gs(c, Ptr3{{c->sw_t, nullptr, nullptr}}, 1)) return 1;
@@ -202,8 +203,8 @@ static int ctx_setup(nlk_ctx* c) {
         NLK_CUDA(cudaMemsetAsync(c->crs_y, 0, nvt * sizeof(double), c->st));
         launch_fill(c->crs_y + v, 1, 1.0, c->st);
         launch_coarse_prolong_add(dm, c->crs_y, c->pw[0], 0, c->st);
-        if (apply_E(c, c->pw[0], c->pw[1])) return 1;
-        launch_coarse_restrict(dm, c->pw[1], c->crs_part, dA0 + (size_t)v * nvt, c->st);
+        if (apply_E(c, c->pw[0], c->pw[1], nullptr)) return 1;
+        launch_coarse_restrict(dm, c->pw[1], nullptr, c->crs_part, dA0 + (size_t)v * nvt, c->st);
       }
       if (ctx_allreduce(c, dA0, (int)(nvt * nvt), false)) return 1;
       std::vector<double> A0((size_t)nvt * nvt);
@@ -248,6 +249,7 @@ int nlk_ctx_create(const nlk_mesh* m, const nlk_params* p, int32_t device, nlk_c
   if (check_device()) return 1;
   if (p->torder < 1 || p->torder > 3) { set_error("torder must be 1..3"); return 1; }
   if (p->lgmres < 1 || p->lgmres > 200) { set_error("lgmres out of range"); return 1; }
+  if (p->pr_proj < 0 || p->pr_proj > 30) { set_error("pr_proj out of range [0,30]"); return 1; }
   NLK_CUDA(cudaSetDevice(device));
   nlk_ctx* c = new nlk_ctx(); c->mesh = m; c->prm = *p; c->device = device;
   NLK_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
@@ -540,7 +542,7 @@ int nlk_test_opgradt(nlk_ctx* c, const double* p, double* wx, double* wy, double
 }
 int nlk_test_cdabdtp(nlk_ctx* c, const double* p, double* ep) {
   if (up(c, c->pw[3], p, c->dm.N2)) return 1;
-  if (apply_E(c, c->pw[3], c->pw[4])) return 1;
+  if (apply_E(c, c->pw[3], c->pw[4], nullptr)) return 1;
   return down(c, ep, c->pw[4], c->dm.N2);
 }
 int nlk_test_convect(nlk_ctx* c, const double* u, const double* cx, const double* cy, const double* cz, double* out) {
@@ -574,7 +576,7 @@ int nlk_test_pressure(nlk_ctx* c, const double* rhs, double tol, double* x, int3
 }
 int nlk_test_precond(nlk_ctx* c, const double* r, double* z) {
   if (up(c, c->pw[3], r, c->dm.N2)) return 1;
-  if (apply_precond(c, c->pw[3], c->pw[4])) return 1;
+  if (apply_precond(c, c->pw[3], c->pw[4], nullptr)) return 1;
   return down(c, z, c->pw[4], c->dm.N2);
 }
 int nlk_test_cfl(nlk_ctx* c, const double* ux, const double* uy, const double* uz, double dt, double* cfl) {
@@ -593,9 +595,9 @@ int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_lau
     switch (which) {
       case 0: launch_axhelm(dm, c->wk[0], c->wk[1], 1.0, 1.0, c->st); break;
       case 1: return ctx_gs(c, Ptr3{{c->wk[0], nullptr, nullptr}}, 1);
-      case 2: return apply_E(c, c->pw[3], c->pw[4]);
+      case 2: return apply_E(c, c->pw[3], c->pw[4], nullptr);
       case 3: launch_convect(dm, CPtr4{{c->wk[3], c->wk[4], c->wk[5], nullptr}}, d, CPtr3{{c->wk[0], c->wk[1], c->wk[2]}}, Ptr4{{c->bf[0], c->bf[1], c->bf[2], nullptr}}, 1.0, 0, c->st); break;
-      case 4: return apply_precond(c, c->pw[3], c->pw[4]);
+      case 4: return apply_precond(c, c->pw[3], c->pw[4], nullptr);
       case 5: { CPtr4 A{{c->wk[0], c->wk[1], c->wk[2], nullptr}}; launch_dot(dm.N1, A, A, d, dm.bm1, c->d_red, c->red, c->st); break; }
       default: set_error("unknown bench kernel"); return 1;
     }

@@ -80,7 +80,7 @@ struct nlk_ctx {
   double* crs_part = nullptr, *crs_r = nullptr, *crs_y = nullptr;
   bool have_coarse = false, have_schwarz = false;
   // pressure projection (residualProj)
-  double* proj_X = nullptr, *proj_EX = nullptr; int nproj = 0;
+  double* proj_X = nullptr, *proj_EX = nullptr, *proj_w = nullptr, *proj_xbar = nullptr; int nproj = 0;
   // time stepping
   double dt = 0; int nsteps = 0; bool adjoint = false;
   // statistics
@@ -116,8 +116,9 @@ int step_setup(nlk_ctx* c, double tau, bool transpose);
 int step_advance(nlk_ctx* c, int istep);
 int helmholtz_solve(nlk_ctx* c, double* rhs_local, double h1, double h2, const double* mask, double tol, double* x, int* iters);
 int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* iters);
-int apply_E(nlk_ctx* c, const double* p, double* ep);
-int apply_precond(nlk_ctx* c, const double* r, double* z);
+int apply_E(nlk_ctx* c, const double* p, double* ep, const double* out_mul);
+int apply_precond(nlk_ctx* c, const double* r, double* z, const double* in_mul);
+int pressure_solve_projected(nlk_ctx* c, double* rhs, double tol, double* x, int* iters);
 int ortho(nlk_ctx* c, double* p);
 int reset_history_pub(nlk_ctx* c);
 void make_filter_matrix(const Basis& b, double w, double cutoff, std::vector<double>& F);

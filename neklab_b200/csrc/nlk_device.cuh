@@ -90,6 +90,7 @@ void launch_lin(double* out, size_t n, double a0, const double* x0, double a1, c
 void launch_fill(double* out, size_t n, double v, cudaStream_t st);
 // K5  opdiv / opgradt (navier1.f multd, cdtp)
 void launch_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, cudaStream_t st);
+void launch_opdiv_fused(const DevMesh& dm, CPtr3 u, double* p, double scale, const double* in_mul, const double* out_mul, cudaStream_t st);
 void launch_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st);
 // K3/K4 convection (convect.f convect_new / convect_adj): out_f (+)= alpha * J^T W[(J C . rx) . grad J u_f]
 void launch_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double alpha, int accumulate, cudaStream_t st);
@@ -110,11 +111,11 @@ void launch_dot(size_t n, CPtr4 a, CPtr4 b, int npairs, const double* c, double*
 void launch_multidot(const double* V, size_t ld, int k, const double* w, size_t n, double* h, Reducer red, cudaStream_t st);
 void launch_multiaxpy(double* w, const double* V, size_t ld, int k, const double* h, double sign, size_t n, cudaStream_t st);
 // K10 Schwarz smoother pieces (hsmg_schwarz / hsmg_fdm / extrude analogues)
-void launch_schwarz_embed(const DevMesh& dm, const double* r, double* w, cudaStream_t st);
+void launch_schwarz_embed(const DevMesh& dm, const double* r, const double* mul, double* w, cudaStream_t st);
 void launch_schwarz_fdm(const DevMesh& dm, const double* w, double* z, double* t, cudaStream_t st);
 void launch_schwarz_gather(const DevMesh& dm, const double* z, const double* t, double* out, cudaStream_t st);
 // K11 coarse grid (crs_solve analogue)
-void launch_coarse_restrict(const DevMesh& dm, const double* r, double* part, double* rc, cudaStream_t st);
+void launch_coarse_restrict(const DevMesh& dm, const double* r, const double* mul, double* part, double* rc, cudaStream_t st);
 void launch_gemv(const double* A, const double* x, double* y, int n, cudaStream_t st);
 void launch_coarse_prolong_add(const DevMesh& dm, const double* c, double* z, int accumulate, cudaStream_t st);
 // K14 compute_cfl
@@ -130,6 +131,8 @@ void launch_unpack_add(double* u, const int32_t* off, const int32_t* idx, int cn
 
 // out = (x0 ? x0 : 0) + a * x1 * m1 * (m2 ? m2 : 1)
 void launch_axpy_mm(double* out, size_t n, const double* x0, double a, const double* x1, const double* m1, const double* m2, cudaStream_t st);
+void launch_multiaxpy_norm(double* w, const double* V, size_t ld, int k, const double* h, double sign, size_t n, double* out, Reducer red, cudaStream_t st);
+void launch_scale_rsqrt(double* out, const double* in, size_t n, const double* s, cudaStream_t st);
 void launch_recip(double* out, const double* x, size_t n, cudaStream_t st);
 void launch_schwarz_count(const DevMesh& dm, const double* w, double* z, double* t, cudaStream_t st);
 void launch_schwarz_gather_nowt(const DevMesh& dm, const double* z, const double* t, double* out, cudaStream_t st);

@@ -299,7 +299,8 @@ __device__ __forceinline__ void load_mat(double* s, const double* g, int cnt) {
 // ------------------------------------------------------------------------------------------------ K5 opdiv / opgradt
 // p = scale * sum_c sum_k rxw2[k][c] * (d_k u_c)|GL     (Nek multd / opdiv); one element per CTA.
 __global__ void k_opdiv(CPtr3 u, double* __restrict__ p, const double* __restrict__ rxw2, const double* __restrict__ I12g,
-                        const double* __restrict__ D12g, int n, int q, int d, double scale) {
+                        const double* __restrict__ D12g, int n, int q, int d, double scale, const double* __restrict__ in_mul, CPtr3 in_mask,
+                        const double* __restrict__ out_mul) {
   extern __shared__ double sm[];
   const int nz = d == 3 ? n : 1, qz = d == 3 ? q : 1;
   const int np1 = n * n * nz, np2 = q * q * qz;
@@ -312,7 +313,8 @@ __global__ void k_opdiv(CPtr3 u, double* __restrict__ p, const double* __restric
   __syncthreads();
   for (int c = 0; c < d; ++c) {
     const double* uc = u.p[c] + e * np1;
-    for (int i = threadIdx.x; i < np1; i += blockDim.x) U[i] = uc[i];
+    if (in_mul) { const double* mk = in_mask.p[c] + e * np1; const double* bi = in_mul + e * np1; for (int i = threadIdx.x; i < np1; i += blockDim.x) U[i] = uc[i] * bi[i] * mk[i]; }
+    else for (int i = threadIdx.x; i < np1; i += blockDim.x) U[i] = uc[i];
     __syncthreads();
     contract<false>(A, U, sDm, q, n, 0, n, n, nz);      // D_x u   (q,n,nz)
     contract<false>(B, U, sI, q, n, 0, n, n, nz);       // I_x u
@@ -334,17 +336,20 @@ __global__ void k_opdiv(CPtr3 u, double* __restrict__ p, const double* __restric
       __syncthreads();
     }
   }
-  for (int i = threadIdx.x; i < np2; i += blockDim.x) p[e * np2 + i] = scale * acc[i];
+  if (out_mul) for (int i = threadIdx.x; i < np2; i += blockDim.x) p[e * np2 + i] = scale * acc[i] * out_mul[e * np2 + i];
+  else for (int i = threadIdx.x; i < np2; i += blockDim.x) p[e * np2 + i] = scale * acc[i];
 }
 static int elem_threads(int np) { int t = ((np + 31) / 32) * 32; return t > 256 ? 256 : (t < 64 ? 64 : t); }
 
-void launch_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, cudaStream_t st) {
+void launch_opdiv_fused(const DevMesh& dm, CPtr3 u, double* p, double scale, const double* in_mul, const double* out_mul, cudaStream_t st) {
   size_t smem = (size_t)(2 * dm.q * dm.n + 7 * dm.np1) * sizeof(double);
   static size_t set = 0;
   if (smem > 48 * 1024 && smem > set) { cudaFuncSetAttribute(k_opdiv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
-  k_opdiv<<<(unsigned)dm.E, elem_threads(dm.np1), smem, st>>>(u, p, dm.rxw2, dm.I12, dm.D12, dm.n, dm.q, dm.ndim, scale);
+  CPtr3 mk{{dm.mask[0], dm.mask[1], dm.mask[2]}};
+  k_opdiv<<<(unsigned)dm.E, elem_threads(dm.np1), smem, st>>>(u, p, dm.rxw2, dm.I12, dm.D12, dm.n, dm.q, dm.ndim, scale, in_mul, mk, out_mul);
   LAUNCH_COUNT();
 }
+void launch_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, cudaStream_t st) { launch_opdiv_fused(dm, u, p, scale, nullptr, nullptr, st); }
 
 // w_c = sum_k (transposed interp/deriv)[ p * rxw2[k][c] ]    (Nek cdtp / opgradt)
 __global__ void k_opgradt(const double* __restrict__ p, Ptr3 w, const double* __restrict__ rxw2, const double* __restrict__ I12tg,
@@ -672,6 +677,33 @@ __global__ void k_multiaxpy(double* __restrict__ w, const double* __restrict__ V
     w[i] = s;
   }
 }
+// w += sign * V h, and out[0] = sum_i w_i^2 of the result (one pass)
+__global__ void __launch_bounds__(256)
+k_multiaxpy_norm(double* __restrict__ w, const double* __restrict__ V, size_t ld, int k, const double* __restrict__ h, double sign, size_t n,
+                 double* out, Reducer red) {
+  extern __shared__ double sh[];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) sh[j] = sign * h[j];
+  __syncthreads();
+  double v[1] = {0.0};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double s = w[i];
+    for (int j = 0; j < k; ++j) s += sh[j] * V[(size_t)j * ld + i];
+    w[i] = s; v[0] += s * s;
+  }
+  if (grid_reduce<1>(v, red)) out[0] = v[0];
+}
+void launch_multiaxpy_norm(double* w, const double* V, size_t ld, int k, const double* h, double sign, size_t n, double* out, Reducer red, cudaStream_t st) {
+  int grid = std::min(cdiv(n, RED_THREADS), RED_BLOCKS);
+  k_multiaxpy_norm<<<grid, RED_THREADS, (k > 0 ? k : 1) * sizeof(double), st>>>(w, V, ld, k, h, sign, n, out, red); LAUNCH_COUNT();
+}
+// out = in * rsqrt(*s)  (zero if *s <= 0): normalisation with a device-resident scalar
+__global__ void k_scale_rsqrt(double* __restrict__ out, const double* __restrict__ in, size_t n, const double* __restrict__ s) {
+  const double sv = *s; const double f = sv > 0 ? rsqrt(sv) : 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i] * f;
+}
+void launch_scale_rsqrt(double* out, const double* in, size_t n, const double* s, cudaStream_t st) {
+  k_scale_rsqrt<<<std::min(cdiv(n, 256), 148 * 8), 256, 0, st>>>(out, in, n, s); LAUNCH_COUNT();
+}
 void launch_multiaxpy(double* w, const double* V, size_t ld, int k, const double* h, double sign, size_t n, cudaStream_t st) {
   if (k <= 0) return;
   k_multiaxpy<<<std::min(cdiv(n, 256), 148 * 8), 256, k * sizeof(double), st>>>(w, V, ld, k, h, sign, n); LAUNCH_COUNT();
@@ -681,7 +713,7 @@ void launch_multiaxpy(double* w, const double* V, size_t ld, int k, const double
 __device__ __forceinline__ int clamp_inner(int i, int n) { return i == 0 ? 1 : (i == n - 1 ? n - 2 : i); }
 
 // w (n^d) <- r (q^d): interior copy; face layers (tangentially interior) = first interior layer; edges/corners = 0
-__global__ void k_schwarz_embed(const double* __restrict__ r, double* __restrict__ w, int n, int d, size_t N1) {
+__global__ void k_schwarz_embed(const double* __restrict__ r, const double* __restrict__ mul, double* __restrict__ w, int n, int d, size_t N1) {
   const int q = n - 2, np1 = d == 3 ? n * n * n : n * n, np2 = d == 3 ? q * q * q : q * q;
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < N1; g += (size_t)gridDim.x * blockDim.x) {
     size_t e = g / np1; int p = (int)(g - e * np1);
@@ -690,13 +722,14 @@ __global__ void k_schwarz_embed(const double* __restrict__ r, double* __restrict
     double v = 0.0;
     if (nb <= 1) {
       int ii = clamp_inner(i, n) - 1, jj = clamp_inner(j, n) - 1, kk = d == 3 ? clamp_inner(k, n) - 1 : 0;
-      v = r[e * np2 + ((size_t)kk * q + jj) * q + ii];
+      size_t s = e * np2 + ((size_t)kk * q + jj) * q + ii;
+      v = mul ? r[s] * mul[s] : r[s];
     }
     w[g] = v;
   }
 }
-void launch_schwarz_embed(const DevMesh& dm, const double* r, double* w, cudaStream_t st) {
-  k_schwarz_embed<<<std::min(cdiv(dm.N1, 256), 148 * 8), 256, 0, st>>>(r, w, dm.n, dm.ndim, dm.N1); LAUNCH_COUNT();
+void launch_schwarz_embed(const DevMesh& dm, const double* r, const double* mul, double* w, cudaStream_t st) {
+  k_schwarz_embed<<<std::min(cdiv(dm.N1, 256), 148 * 8), 256, 0, st>>>(r, mul, w, dm.n, dm.ndim, dm.N1); LAUNCH_COUNT();
 }
 
 // per element: face fix (w_face -= w_inner), z = (S (x) S (x) S) dinv (S^T (x) S^T (x) S^T) w ; t = z on faces else 0.
@@ -787,13 +820,14 @@ __device__ __forceinline__ double corner_shape(int c, int p, int q, int d, const
   double hz = d == 3 ? (((c >> 2) & 1) ? 0.5 * (1 + z2[k]) : 0.5 * (1 - z2[k])) : 1.0;
   return hx * hy * hz;
 }
-__global__ void k_coarse_part(const double* __restrict__ r, double* __restrict__ part, const double* __restrict__ z2, int q, int d, size_t nec) {
+__global__ void k_coarse_part(const double* __restrict__ r, const double* __restrict__ mul, double* __restrict__ part, const double* __restrict__ z2, int q, int d, size_t nec) {
   const int nv = 1 << d, np2 = d == 3 ? q * q * q : q * q;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nec) return;
   size_t e = t / nv; int c = (int)(t % nv);
   double s = 0;
-  for (int p = 0; p < np2; ++p) s += corner_shape(c, p, q, d, z2) * r[e * np2 + p];
+  if (mul) for (int p = 0; p < np2; ++p) s += corner_shape(c, p, q, d, z2) * r[e * np2 + p] * mul[e * np2 + p];
+  else for (int p = 0; p < np2; ++p) s += corner_shape(c, p, q, d, z2) * r[e * np2 + p];
   part[t] = s;
 }
 __global__ void k_vert_gather(const double* __restrict__ part, const int32_t* __restrict__ off, const int32_t* __restrict__ ec, double* __restrict__ rc, int64_t nvert) {
@@ -803,9 +837,9 @@ __global__ void k_vert_gather(const double* __restrict__ part, const int32_t* __
   for (int t = off[v]; t < off[v + 1]; ++t) s += part[ec[t]];
   rc[v] = s;
 }
-void launch_coarse_restrict(const DevMesh& dm, const double* r, double* part, double* rc, cudaStream_t st) {
+void launch_coarse_restrict(const DevMesh& dm, const double* r, const double* mul, double* part, double* rc, cudaStream_t st) {
   size_t nec = (size_t)dm.E << dm.ndim;
-  k_coarse_part<<<cdiv(nec, 128), 128, 0, st>>>(r, part, dm.w2 + dm.q, dm.q, dm.ndim, nec); LAUNCH_COUNT();
+  k_coarse_part<<<cdiv(nec, 128), 128, 0, st>>>(r, mul, part, dm.w2 + dm.q, dm.q, dm.ndim, nec); LAUNCH_COUNT();
   k_vert_gather<<<cdiv(dm.nvert, 128), 128, 0, st>>>(part, dm.vert_off, dm.vert_ec, rc, dm.nvert); LAUNCH_COUNT();
 }
 __global__ void k_gemv(const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y, int n) {

@@ -141,14 +141,13 @@ static void filter_matrix(const Basis& b, double wght, double cutoff, std::vecto
 }
 
 // ------------------------------------------------------------------------------------------------ operators
-int apply_E(nlk_ctx* c, const double* p, double* ep) {       // Nek cdabdtp, intype = 1
+int apply_E(nlk_ctx* c, const double* p, double* ep, const double* out_mul) {       // Nek cdabdtp, intype = 1
   const DevMesh& dm = c->dm; const int d = dm.ndim;
   Ptr3 w{{c->wk[0], c->wk[1], c->wk[2]}};
   launch_opgradt(dm, p, w, c->st);
   if (ctx_gs(c, w, d)) return 1;
-  for (int k = 0; k < d; ++k) launch_axpy_mm(w.p[k], dm.N1, nullptr, 1.0 / c->prm.density, w.p[k], dm.binvm1, dm.mask[k], c->st);   // opbinv
   CPtr3 cw{{w.p[0], w.p[1], w.p[2]}};
-  launch_opdiv(dm, cw, ep, 1.0, c->st);
+  launch_opdiv_fused(dm, cw, ep, 1.0 / c->prm.density, dm.binvm1, out_mul, c->st);      // opbinv (binvm1*mask/rho) fused into the load
   return 0;
 }
 
@@ -159,20 +158,21 @@ int ortho(nlk_ctx* c, double* p) {                           // Nek ortho: remov
   return 0;
 }
 
-int apply_precond(nlk_ctx* c, const double* r, double* z) {
+int apply_precond(nlk_ctx* c, const double* r, double* z, const double* in_mul) {     // z = M^-1 (in_mul * r)
   const DevMesh& dm = c->dm;
   if (!c->have_schwarz) {                                   // mass-scaled identity
     launch_lin(z, dm.N2, 1.0, r, 0, nullptr, 0, nullptr, 0, nullptr, c->pw[5], c->st);   // pw[5] holds 1/bm2
+    if (in_mul) launch_lin(z, dm.N2, 1.0, z, 0, nullptr, 0, nullptr, 0, nullptr, in_mul, c->st);
     return 0;
   }
-  launch_schwarz_embed(dm, r, c->sw_w, c->st);
+  launch_schwarz_embed(dm, r, in_mul, c->sw_w, c->st);
   if (ctx_gs(c, Ptr3{{c->sw_w, nullptr, nullptr}}, 1)) return 1;
   launch_schwarz_fdm(dm, c->sw_w, c->sw_z, c->sw_t, c->st);
   if (ctx_gs(c, Ptr3{{c->sw_t, nullptr, nullptr}}, 1)) return 1;
   launch_schwarz_gather(dm, c->sw_z, c->sw_t, z, c->st);
   if (c->prm.precond == 3) launch_fill(z, dm.N2, 0.0, c->st);     // debug: coarse term only
   if (c->have_coarse) {
-    launch_coarse_restrict(dm, r, c->crs_part, c->crs_r, c->st);
+    launch_coarse_restrict(dm, r, in_mul, c->crs_part, c->crs_r, c->st);
     if (ctx_allreduce(c, c->crs_r, (int)dm.nvert, false)) return 1;
     launch_gemv(dm.A0inv, c->crs_r, c->crs_y, (int)dm.nvert, c->st);
     launch_coarse_prolong_add(dm, c->crs_y, z, 1, c->st);
@@ -228,7 +228,7 @@ int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* it
   double* dh = c->d_red;          // device scalars: h[0..m), alpha2 at [m]
   while (!conv && iter < maxit) {
     if (iter == 0) launch_lin(r, N2, 1.0, rhs, 0, nullptr, 0, nullptr, 0, nullptr, dm.ml, c->st);
-    else { if (apply_E(c, x, w)) return 1; launch_lin(r, N2, 1.0, rhs, -1.0, w, 0, nullptr, 0, nullptr, dm.ml, c->st); }
+    else { if (apply_E(c, x, w, nullptr)) return 1; launch_lin(r, N2, 1.0, rhs, -1.0, w, 0, nullptr, 0, nullptr, dm.ml, c->st); }
     if (global_dot(c, N2, r, r, nullptr, dh)) return 1;
     if (ctx_read_scalars(c, 1)) return 1;
     gamma[0] = std::sqrt(c->h_red[0]);
@@ -239,15 +239,14 @@ int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* it
     for (j = 1; j <= m; ++j) {
       ++iter;
       double* vj = c->gm_V + (size_t)(j - 1) * N2; double* zj = c->gm_Z + (size_t)(j - 1) * N2;
-      launch_lin(tmp, N2, 1.0, vj, 0, nullptr, 0, nullptr, 0, nullptr, dm.mu, c->st);
-      if (apply_precond(c, tmp, zj)) return 1;
+      (void)tmp;
+      if (apply_precond(c, vj, zj, dm.mu)) return 1;                          // z = M^-1 (mu v)
       if (ortho(c, zj)) return 1;
-      if (apply_E(c, zj, w)) return 1;
-      launch_lin(w, N2, 1.0, w, 0, nullptr, 0, nullptr, 0, nullptr, dm.ml, c->st);
+      if (apply_E(c, zj, w, dm.ml)) return 1;                                 // w = ml * E z
       launch_multidot(c->gm_V, N2, j, w, N2, dh, c->red, c->st);
       if (ctx_allreduce(c, dh, j, false)) return 1;
-      launch_multiaxpy(w, c->gm_V, N2, j, dh, -1.0, N2, c->st);
-      if (global_dot(c, N2, w, w, nullptr, dh + m)) return 1;
+      launch_multiaxpy_norm(w, c->gm_V, N2, j, dh, -1.0, N2, dh + m, c->red, c->st);   // w -= V h ; |w|^2
+      if (ctx_allreduce(c, dh + m, 1, false)) return 1;
       if (ctx_read_scalars(c, m + 1)) return 1;
       for (int i = 0; i < j; ++i) H[(size_t)i * m + (j - 1)] = c->h_red[i];
       for (int i = 0; i < j - 1; ++i) {
@@ -279,6 +278,50 @@ int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* it
   if (ortho(c, x)) return 1;
   if (iters) *iters = iter;
   c->gmres_iters += iter;
+  return 0;
+}
+
+// Pressure residual projection (Nek `setrhsp`/`gensolnp`, .par residualProj = yes, SIZE mxprev): the rhs is projected onto
+// the span of up to pr_proj previous solutions kept E-orthonormal (X^T E X = I); both X and E X are stored so the
+// projection costs two tall-skinny passes and the basis update one extra E-apply.  Reset at every matvec start.
+int pressure_solve_projected(nlk_ctx* c, double* rhs, double tol, double* x, int* iters) {
+  const DevMesh& dm = c->dm; const size_t N2 = dm.N2; const int mx = c->prm.pr_proj;
+  if (mx <= 0) return pressure_solve(c, rhs, tol, x, iters);
+  double* al = c->d_red + 400; double* be = c->d_red + 432; double* nr = c->d_red + 464;
+  int m = c->nproj;
+  if (m > 0) {
+    launch_multidot(c->proj_X, N2, m, rhs, N2, al, c->red, c->st);
+    if (ctx_allreduce(c, al, m, false)) return 1;
+    launch_fill(c->proj_xbar, N2, 0.0, c->st);
+    launch_multiaxpy(c->proj_xbar, c->proj_X, N2, m, al, 1.0, N2, c->st);
+    launch_multiaxpy(rhs, c->proj_EX, N2, m, al, -1.0, N2, c->st);
+  }
+  if (pressure_solve(c, rhs, tol, x, iters)) return 1;                      // x = delta
+  double* w = c->proj_w;
+  if (m == mx) {                                                            // restart the space with the full solution
+    launch_lin(x, N2, 1.0, x, 1.0, c->proj_xbar, 0, nullptr, 0, nullptr, nullptr, c->st);
+    if (apply_E(c, x, w, nullptr)) return 1;
+    if (global_dot(c, N2, x, w, nullptr, nr)) return 1;
+    launch_scale_rsqrt(c->proj_X, x, N2, nr, c->st);
+    launch_scale_rsqrt(c->proj_EX, w, N2, nr, c->st);
+    c->nproj = 1;
+    return 0;
+  }
+  // E-orthonormalise delta against X and append
+  double* dl = c->proj_X + (size_t)m * N2; double* edl = c->proj_EX + (size_t)m * N2;
+  if (apply_E(c, x, w, nullptr)) return 1;
+  NLK_CUDA(cudaMemcpyAsync(dl, x, N2 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+  if (m > 0) {
+    launch_multidot(c->proj_X, N2, m, w, N2, be, c->red, c->st);
+    if (ctx_allreduce(c, be, m, false)) return 1;
+    launch_multiaxpy(dl, c->proj_X, N2, m, be, -1.0, N2, c->st);
+    launch_multiaxpy(w, c->proj_EX, N2, m, be, -1.0, N2, c->st);
+  }
+  if (global_dot(c, N2, dl, w, nullptr, nr)) return 1;
+  launch_scale_rsqrt(dl, dl, N2, nr, c->st);
+  launch_scale_rsqrt(edl, w, N2, nr, c->st);
+  c->nproj = m + 1;
+  if (m > 0) launch_lin(x, N2, 1.0, x, 1.0, c->proj_xbar, 0, nullptr, 0, nullptr, nullptr, c->st);    // full solution
   return 0;
 }
 
@@ -396,7 +439,7 @@ int step_advance(nlk_ctx* c, int istep) {
   NLK_CUDA(cudaMemcpyAsync(c->prlag, c->prp, dm.N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));                            // lagpresp
   NLK_CUDA(cudaMemcpyAsync(c->prp, pext, dm.N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));                                // up = prextr (+ dp below)
   double* xs = c->pw[3];                                                                                                        // pext is dead from here
-  if (pressure_solve(c, rhs, P.ptol, xs, nullptr)) return 1;
+  if (pressure_solve_projected(c, rhs, P.ptol, xs, nullptr)) return 1;
   launch_lin(c->prp, dm.N2, 1.0, c->prp, bd[0] / dt, xs, 0, nullptr, 0, nullptr, nullptr, st);                                  // add3(up, prextr, dp)
   Ptr3 w{{c->wk[0], c->wk[1], c->wk[2]}};
   launch_opgradt(dm, xs, w, st);

@@ -37,6 +37,7 @@ CASES = {
     "box2d_outflow_bdf3": dict(mesh=dict(ndim=2, nel=(4, 3), n=6, lxd=9, bc={"xlo": "v  ", "xhi": "O  "}), torder=3, tau=0.25),
     "box2d_periodic_bdf2": dict(mesh=dict(ndim=2, nel=(4, 4), n=6, lxd=9, periodic=[True, False]), torder=2, tau=0.2),
     "box3d_bdf3": dict(mesh=dict(ndim=3, nel=(3, 2, 2), n=5, lxd=8, bc={"xlo": "v  ", "xhi": "O  "}), torder=3, tau=0.1),
+    "box2d_outflow_bdf3_proj": dict(mesh=dict(ndim=2, nel=(4, 3), n=6, lxd=9, bc={"xlo": "v  ", "xhi": "O  "}), torder=3, tau=0.25, proj=8),
 }
 
 
@@ -52,7 +53,8 @@ def setup(request, nlk_lib):
     st = PertStepper(om, prm, precond=pc)
     bf = _baseflow(om)
     A_or = ExptA(st, cfg["tau"], bf)
-    ctx = api.Context(m, api.default_params(viscosity=nu, torder=cfg["torder"], vtol=1e-13, ptol=1e-13, gmres_maxit=2000, cg_maxit=2000))
+    ctx = api.Context(m, api.default_params(viscosity=nu, torder=cfg["torder"], vtol=1e-13, ptol=1e-13, gmres_maxit=2000, cg_maxit=2000,
+                                            pr_proj=cfg.get("proj", 0)))
     A_dev = api.exptA_linop(ctx, cfg["tau"], _to_dev(ctx, bf))
     yield request.param, om, ctx, A_or, A_dev, cfg
     ctx.close()
