@@ -83,7 +83,7 @@ static int ctx_setup(nlk_ctx* c) {
   if (dev_alloc(c, &c->d_sc, 1) || dev_alloc(c, &c->d_red, 512)) return 1;
   NLK_CUDA(cudaMallocHost((void**)&c->h_sc, sizeof(SolverScal)));
   NLK_CUDA(cudaMallocHost((void**)&c->h_red, sizeof(double) * 512));
-  c->red.maxblocks = 1024;
+  c->red.maxblocks = 2048;
   if (dev_alloc(c, &c->red.partial, (size_t)16 * c->red.maxblocks) || dev_alloc(c, &c->red.counter, 1)) return 1;
   // state + work arrays
   for (int k = 0; k < 3; ++k) {

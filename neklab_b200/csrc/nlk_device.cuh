@@ -139,6 +139,12 @@ void launch_schwarz_gather_nowt(const DevMesh& dm, const double* z, const double
 void launch_rand_field_impl(double* out, const double* x, const double* y, const double* z, const int64_t* lglel, int np1, size_t N1,
                             uint64_t seed, int comp, cudaStream_t st);
 void launch_cg_finalize(SolverScal* sc, int which, double vol, cudaStream_t st);
+// compile-time-sized versions (nlk_kernels_tp.cu); return false when (lx1, lxd) has no instantiation -> runtime fallback
+bool tp_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, const double* in_mul, const double* out_mul, cudaStream_t st);
+bool tp_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st);
+bool tp_schwarz_fdm(const DevMesh& dm, const double* w, double* z, double* t, cudaStream_t st);
+bool tp_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double alpha, int accumulate, cudaStream_t st);
+bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st);
 extern thread_local long g_launches;   // counts kernel launches issued through these wrappers
 
 }  // namespace nlk

@@ -9,7 +9,7 @@ thread_local long g_launches = 0;
 #define LAUNCH_COUNT() (++g_launches)
 
 static inline int cdiv(size_t a, size_t b) { return (int)((a + b - 1) / b); }
-static const int RED_BLOCKS = 592;   // 148 SMs x 4
+static const int RED_BLOCKS = 1184;  // 148 SMs x 8
 static const int RED_THREADS = 256;
 
 // ------------------------------------------------------------------------------------------------ reductions
@@ -231,6 +231,7 @@ void launch_unpack_add(double* u, const int32_t* off, const int32_t* idx, int cn
 // ------------------------------------------------------------------------------------------------ pointwise
 __global__ void k_lin(double* __restrict__ out, size_t n, double a0, const double* __restrict__ x0, double a1, const double* __restrict__ x1,
                       double a2, const double* __restrict__ x2, double a3, const double* __restrict__ x3, const double* __restrict__ mul) {
+#pragma unroll 4
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double v = 0;
     if (x0) v += a0 * x0[i];
@@ -249,6 +250,7 @@ void launch_lin(double* out, size_t n, double a0, const double* x0, double a1, c
 }
 __global__ void k_axpy_mm(double* __restrict__ out, size_t n, const double* __restrict__ x0, double a, const double* __restrict__ x1,
                           const double* __restrict__ m1, const double* __restrict__ m2) {
+#pragma unroll 4
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double v = a * x1[i] * m1[i];
     if (m2) v *= m2[i];
@@ -342,6 +344,7 @@ __global__ void k_opdiv(CPtr3 u, double* __restrict__ p, const double* __restric
 static int elem_threads(int np) { int t = ((np + 31) / 32) * 32; return t > 256 ? 256 : (t < 64 ? 64 : t); }
 
 void launch_opdiv_fused(const DevMesh& dm, CPtr3 u, double* p, double scale, const double* in_mul, const double* out_mul, cudaStream_t st) {
+  if (tp_opdiv(dm, u, p, scale, in_mul, out_mul, st)) return;
   size_t smem = (size_t)(2 * dm.q * dm.n + 7 * dm.np1) * sizeof(double);
   static size_t set = 0;
   if (smem > 48 * 1024 && smem > set) { cudaFuncSetAttribute(k_opdiv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
@@ -395,6 +398,7 @@ __global__ void k_opgradt(const double* __restrict__ p, Ptr3 w, const double* __
   }
 }
 void launch_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st) {
+  if (tp_opgradt(dm, p, w, st)) return;
   size_t smem = (size_t)(2 * dm.q * dm.n + 7 * dm.np1) * sizeof(double);
   static size_t set = 0;
   if (smem > 48 * 1024 && smem > set) { cudaFuncSetAttribute(k_opgradt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
@@ -479,6 +483,7 @@ __global__ void k_convect(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __re
   }
 }
 void launch_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double alpha, int accumulate, cudaStream_t st) {
+  if (tp_convect(dm, u, nf, C, out, alpha, accumulate, st)) return;
   size_t smem = (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * dm.npd) * sizeof(double);
   static size_t set = 0;
   if (smem > 48 * 1024 && smem > set) { cudaFuncSetAttribute(k_convect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
@@ -529,6 +534,7 @@ __global__ void k_convect_adj(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __restr
   }
 }
 void launch_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st) {
+  if (tp_convect_adj(dm, U, c, out, alpha, accumulate, st)) return;
   size_t smem = (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * dm.npd) * sizeof(double);
   static size_t set = 0;
   if (smem > 48 * 1024 && smem > set) { cudaFuncSetAttribute(k_convect_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
@@ -543,6 +549,7 @@ __global__ void k_rhs_tail(RhsTail t, size_t n, const double* __restrict__ bm1, 
   const int f = blockIdx.y;
   double* bf = t.bf[f]; double* e1 = t.e1[f]; double* e2 = t.e2[f]; const double* u = t.u[f]; double* l1 = t.lag1[f]; double* l2 = t.lag2[f];
   const double coef = t.coef[f];
+#pragma unroll 4
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double b = bf[i], x1 = e1[i], x2 = e2[i], uu = u[i], a1 = l1[i], a2 = l2[i];
     e2[i] = x1; e1[i] = b;
@@ -595,6 +602,7 @@ k_cg_update_reduce(double* __restrict__ x, double* __restrict__ r, const double*
   if (sc->done) return;
   const double alpha = first ? 0.0 : sc->alpha;
   double v[2] = {0.0, 0.0};
+#pragma unroll 4
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double ri = r[i];
     if (!first) {
@@ -635,6 +643,7 @@ void launch_cg_pap(const DevMesh& dm, const double* w, const double* p, const do
 __global__ void __launch_bounds__(256)
 k_dot(size_t n, CPtr4 a, CPtr4 b, int npairs, const double* __restrict__ c, double* out, Reducer red) {
   double v[1] = {0.0};
+#pragma unroll 4
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double s = 0;
     for (int k = 0; k < npairs; ++k) s += a.p[k][i] * b.p[k][i];
@@ -654,6 +663,7 @@ k_multidot(const double* __restrict__ V, size_t ld, int k0, int k, const double*
   double v[KB];
 #pragma unroll
   for (int j = 0; j < KB; ++j) v[j] = 0.0;
+#pragma unroll 4
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double wi = w[i];
 #pragma unroll
@@ -671,6 +681,7 @@ __global__ void k_multiaxpy(double* __restrict__ w, const double* __restrict__ V
   extern __shared__ double sh[];
   for (int j = threadIdx.x; j < k; j += blockDim.x) sh[j] = sign * h[j];
   __syncthreads();
+#pragma unroll 4
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double s = w[i];
     for (int j = 0; j < k; ++j) s += sh[j] * V[(size_t)j * ld + i];
@@ -685,6 +696,7 @@ k_multiaxpy_norm(double* __restrict__ w, const double* __restrict__ V, size_t ld
   for (int j = threadIdx.x; j < k; j += blockDim.x) sh[j] = sign * h[j];
   __syncthreads();
   double v[1] = {0.0};
+#pragma unroll 4
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double s = w[i];
     for (int j = 0; j < k; ++j) s += sh[j] * V[(size_t)j * ld + i];
@@ -776,6 +788,7 @@ __global__ void k_schwarz_fdm(const double* __restrict__ w, double* __restrict__
   }
 }
 void launch_schwarz_fdm(const DevMesh& dm, const double* w, double* z, double* t, cudaStream_t st) {
+  if (tp_schwarz_fdm(dm, w, z, t, st)) return;
   size_t smem = (size_t)(2 * dm.ndim * dm.n * dm.n + 2 * dm.np1) * sizeof(double);
   k_schwarz_fdm<<<(unsigned)dm.E, elem_threads(dm.np1), smem, st>>>(w, z, t, dm.fdmS, dm.fdmSt, dm.fdmDinv, dm.n, dm.ndim); LAUNCH_COUNT();
 }

@@ -1,0 +1,375 @@
+// Compile-time-sized tensor-product kernels (K3/K4/K5/K10/K15) for sm_100a.
+// Each 1-D contraction is "pencil"-tiled in 3-D: one thread loads the MI inputs of a pencil into registers and produces
+// all MO outputs (MO*MI FMAs per MI shared-memory loads, operator matrix read as a warp broadcast), so the kernels are
+// bounded by HBM traffic of the element data rather than by shared-memory bandwidth.  In 2-D (few pencils) one thread
+// per output point with fully unrolled loops is used.  Runtime-sized fallbacks live in nlk_kernels.cu.
+#include "nlk_device.cuh"
+
+namespace nlk {
+
+template <int MO, int MI, int DIR, bool ACC, int N0, int N1, int N2>
+__device__ __forceinline__ void contract_t(double* __restrict__ out, const double* __restrict__ in, const double* __restrict__ M) {
+  constexpr int O0 = DIR == 0 ? MO : N0, O1 = DIR == 1 ? MO : N1, O2 = DIR == 2 ? MO : N2;
+  constexpr int P0 = DIR == 0 ? 1 : N0, P1 = DIR == 1 ? 1 : N1, P2 = DIR == 2 ? 1 : N2;
+  constexpr int NPEN = P0 * P1 * P2;
+  constexpr int istr = DIR == 0 ? 1 : (DIR == 1 ? N0 : N0 * N1);
+  constexpr int ostr = DIR == 0 ? 1 : (DIR == 1 ? O0 : O0 * O1);
+  if constexpr (NPEN >= 32) {
+    for (int t = threadIdx.x; t < NPEN; t += blockDim.x) {
+      const int a = t % P0, b = (t / P0) % P1, c = t / (P0 * P1);
+      const int ibase = a + N0 * (b + N1 * c), obase = a + O0 * (b + O1 * c);
+      double r[MI];
+#pragma unroll
+      for (int l = 0; l < MI; ++l) r[l] = in[ibase + l * istr];
+#pragma unroll
+      for (int o = 0; o < MO; ++o) {
+        double s = 0;
+#pragma unroll
+        for (int l = 0; l < MI; ++l) s += M[o * MI + l] * r[l];
+        if (ACC) out[obase + o * ostr] += s; else out[obase + o * ostr] = s;
+      }
+    }
+  } else {
+    constexpr int TOT = O0 * O1 * O2;
+    for (int idx = threadIdx.x; idx < TOT; idx += blockDim.x) {
+      const int i = idx % O0, j = (idx / O0) % O1, k = idx / (O0 * O1);
+      const int r = DIR == 0 ? i : (DIR == 1 ? j : k);
+      const int base = (DIR == 0 ? 0 : i) + N0 * ((DIR == 1 ? 0 : j) + N1 * (DIR == 2 ? 0 : k));
+      double s = 0;
+#pragma unroll
+      for (int l = 0; l < MI; ++l) s += M[r * MI + l] * in[base + l * istr];
+      if (ACC) out[idx] += s; else out[idx] = s;
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void load_mat_t(double* s, const double* g, int cnt) {
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) s[i] = g[i];
+}
+static inline int tp_threads(int nmax, int d, int np) {
+  if (d == 3) { int t = ((nmax * nmax + 31) / 32) * 32; return t > 256 ? 256 : t; }
+  int t = ((np + 31) / 32) * 32; return t > 256 ? 256 : (t < 64 ? 64 : t);
+}
+
+// ------------------------------------------------------------------------------------------------ K5 opdiv
+template <int N, int DIM>
+__global__ void k_opdiv_t(CPtr3 u, double* __restrict__ p, const double* __restrict__ rxw2, const double* __restrict__ I12g,
+                          const double* __restrict__ D12g, double scale, const double* __restrict__ in_mul, CPtr3 in_mask,
+                          const double* __restrict__ out_mul) {
+  constexpr int n = N, q = N - 2, d = DIM, nz = DIM == 3 ? N : 1, qz = DIM == 3 ? q : 1;
+  constexpr int np1 = n * n * nz, np2 = q * q * qz;
+  extern __shared__ double sm[];
+  double* sI = sm; double* sDm = sI + q * n;
+  double* U = sDm + q * n; double* A = U + np1; double* B = A + np1; double* T0 = B + np1; double* T1 = T0 + np1; double* T2 = T1 + np1;
+  double* acc = T2 + np1;
+  const size_t e = blockIdx.x;
+  load_mat_t(sI, I12g, q * n); load_mat_t(sDm, D12g, q * n);
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) acc[i] = 0.0;
+  __syncthreads();
+  const double* rw = rxw2 + e * (size_t)(d * d) * np2;
+#pragma unroll 1
+  for (int c = 0; c < d; ++c) {
+    const double* uc = u.p[c] + e * np1;
+    if (in_mul) { const double* mk = in_mask.p[c] + e * np1; const double* bi = in_mul + e * np1; for (int i = threadIdx.x; i < np1; i += blockDim.x) U[i] = uc[i] * bi[i] * mk[i]; }
+    else for (int i = threadIdx.x; i < np1; i += blockDim.x) U[i] = uc[i];
+    __syncthreads();
+    contract_t<q, n, 0, false, n, n, nz>(A, U, sDm);
+    contract_t<q, n, 0, false, n, n, nz>(B, U, sI);
+    if constexpr (DIM == 2) {
+      contract_t<q, n, 1, false, q, n, 1>(T0, A, sI);
+      contract_t<q, n, 1, false, q, n, 1>(T1, B, sDm);
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) acc[i] += rw[(0 * d + c) * np2 + i] * T0[i] + rw[(1 * d + c) * np2 + i] * T1[i];
+      __syncthreads();
+    } else {
+      contract_t<q, n, 1, false, q, n, n>(T0, A, sI);
+      contract_t<q, n, 1, false, q, n, n>(T1, B, sDm);
+      contract_t<q, n, 1, false, q, n, n>(T2, B, sI);
+      contract_t<q, n, 2, false, q, q, n>(A, T0, sI);
+      contract_t<q, n, 2, false, q, q, n>(B, T1, sI);
+      contract_t<q, n, 2, false, q, q, n>(U, T2, sDm);
+      for (int i = threadIdx.x; i < np2; i += blockDim.x)
+        acc[i] += rw[(0 * d + c) * np2 + i] * A[i] + rw[(1 * d + c) * np2 + i] * B[i] + rw[(2 * d + c) * np2 + i] * U[i];
+      __syncthreads();
+    }
+  }
+  if (out_mul) for (int i = threadIdx.x; i < np2; i += blockDim.x) p[e * np2 + i] = scale * acc[i] * out_mul[e * np2 + i];
+  else for (int i = threadIdx.x; i < np2; i += blockDim.x) p[e * np2 + i] = scale * acc[i];
+}
+
+// ------------------------------------------------------------------------------------------------ K5 opgradt
+template <int N, int DIM>
+__global__ void k_opgradt_t(const double* __restrict__ p, Ptr3 w, const double* __restrict__ rxw2, const double* __restrict__ I12tg,
+                            const double* __restrict__ D12tg) {
+  constexpr int n = N, q = N - 2, d = DIM, nz = DIM == 3 ? N : 1, qz = DIM == 3 ? q : 1;
+  constexpr int np1 = n * n * nz, np2 = q * q * qz;
+  extern __shared__ double sm[];
+  double* sIt = sm; double* sDt = sIt + q * n;
+  double* P = sDt + q * n; double* S0 = P + np1; double* S1 = S0 + np1; double* S2 = S1 + np1; double* A0 = S2 + np1; double* A1 = A0 + np1;
+  double* A2 = A1 + np1;
+  const size_t e = blockIdx.x;
+  load_mat_t(sIt, I12tg, q * n); load_mat_t(sDt, D12tg, q * n);
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) P[i] = p[e * np2 + i];
+  __syncthreads();
+  const double* rw = rxw2 + e * (size_t)(d * d) * np2;
+#pragma unroll 1
+  for (int c = 0; c < d; ++c) {
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+      S0[i] = P[i] * rw[(0 * d + c) * np2 + i];
+      S1[i] = P[i] * rw[(1 * d + c) * np2 + i];
+      if (d == 3) S2[i] = P[i] * rw[(2 * d + c) * np2 + i];
+    }
+    __syncthreads();
+    double* wc = w.p[c] + e * np1;
+    if constexpr (DIM == 2) {
+      contract_t<n, q, 0, false, q, q, 1>(A0, S0, sDt);
+      contract_t<n, q, 0, false, q, q, 1>(A1, S1, sIt);
+      contract_t<n, q, 1, false, n, q, 1>(S0, A0, sIt);
+      contract_t<n, q, 1, true, n, q, 1>(S0, A1, sDt);
+      for (int i = threadIdx.x; i < np1; i += blockDim.x) wc[i] = S0[i];
+      __syncthreads();
+    } else {
+      contract_t<n, q, 0, false, q, q, q>(A0, S0, sDt);
+      contract_t<n, q, 0, false, q, q, q>(A1, S1, sIt);
+      contract_t<n, q, 0, false, q, q, q>(A2, S2, sIt);
+      contract_t<n, q, 1, false, n, q, q>(S0, A0, sIt);
+      contract_t<n, q, 1, true, n, q, q>(S0, A1, sDt);
+      contract_t<n, q, 1, false, n, q, q>(S1, A2, sIt);
+      contract_t<n, q, 2, false, n, n, q>(A0, S0, sIt);
+      contract_t<n, q, 2, true, n, n, q>(A0, S1, sDt);
+      for (int i = threadIdx.x; i < np1; i += blockDim.x) wc[i] = A0[i];
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K3 convect
+template <int N, int MD, int DIM>
+__global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __restrict__ rxd, const double* __restrict__ I1dg,
+                            const double* __restrict__ I1dtg, const double* __restrict__ Ddg, double alpha, int accumulate) {
+  constexpr int n = N, m = MD, d = DIM, nz = DIM == 3 ? N : 1, mz = DIM == 3 ? MD : 1;
+  constexpr int np1 = n * n * nz, npd = m * m * mz;
+  extern __shared__ double sm[];
+  double* sI = sm; double* sIt = sI + m * n; double* sDd = sIt + m * n;
+  double* TR = sDd + m * m; double* UF = TR + 3 * npd; double* W1 = UF + npd; double* W2 = W1 + npd; double* ACC = W2 + npd;
+  const size_t e = blockIdx.x;
+  load_mat_t(sI, I1dg, m * n); load_mat_t(sIt, I1dtg, m * n); load_mat_t(sDd, Ddg, m * m);
+  __syncthreads();
+#pragma unroll 1
+  for (int c = 0; c < d; ++c) {
+    const double* cc = C.p[c] + e * np1;
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = cc[i];
+    __syncthreads();
+    if constexpr (DIM == 2) {
+      contract_t<m, n, 0, false, n, n, 1>(W2, W1, sI);
+      contract_t<m, n, 1, false, m, n, 1>(TR + c * npd, W2, sI);
+    } else {
+      contract_t<m, n, 0, false, n, n, n>(W2, W1, sI);
+      contract_t<m, n, 1, false, m, n, n>(W1, W2, sI);
+      contract_t<m, n, 2, false, m, m, n>(TR + c * npd, W1, sI);
+    }
+  }
+  const double* rx = rxd + e * (size_t)(d * d) * npd;
+  for (int i = threadIdx.x; i < npd; i += blockDim.x) {
+    double cf[3] = {TR[i], TR[npd + i], d == 3 ? TR[2 * npd + i] : 0.0};
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+      double s = 0;
+#pragma unroll
+      for (int c = 0; c < d; ++c) s += rx[(k * d + c) * npd + i] * cf[c];
+      TR[k * npd + i] = s;
+    }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int f = 0; f < nf; ++f) {
+    const double* uf = u.p[f] + e * np1;
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = uf[i];
+    __syncthreads();
+    if constexpr (DIM == 2) {
+      contract_t<m, n, 0, false, n, n, 1>(W2, W1, sI);
+      contract_t<m, n, 1, false, m, n, 1>(UF, W2, sI);
+      contract_t<m, m, 0, false, m, m, 1>(W1, UF, sDd);
+      contract_t<m, m, 1, false, m, m, 1>(W2, UF, sDd);
+      for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] = TR[i] * W1[i] + TR[npd + i] * W2[i];
+      __syncthreads();
+      contract_t<n, m, 0, false, m, m, 1>(W1, ACC, sIt);
+      contract_t<n, m, 1, false, n, m, 1>(W2, W1, sIt);
+    } else {
+      contract_t<m, n, 0, false, n, n, n>(W2, W1, sI);
+      contract_t<m, n, 1, false, m, n, n>(W1, W2, sI);
+      contract_t<m, n, 2, false, m, m, n>(UF, W1, sI);
+      contract_t<m, m, 0, false, m, m, m>(W1, UF, sDd);
+      for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] = TR[i] * W1[i];
+      __syncthreads();
+      contract_t<m, m, 1, false, m, m, m>(W1, UF, sDd);
+      for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] += TR[npd + i] * W1[i];
+      __syncthreads();
+      contract_t<m, m, 2, false, m, m, m>(W1, UF, sDd);
+      for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] += TR[2 * npd + i] * W1[i];
+      __syncthreads();
+      contract_t<n, m, 0, false, m, m, m>(W1, ACC, sIt);
+      contract_t<n, m, 1, false, n, m, m>(UF, W1, sIt);
+      contract_t<n, m, 2, false, n, n, m>(W2, UF, sIt);
+    }
+    double* of = out.p[f] + e * np1;
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[i];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K4 convect_adj
+template <int N, int MD, int DIM>
+__global__ void k_convect_adj_t(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __restrict__ rxd, const double* __restrict__ I1dg,
+                                const double* __restrict__ I1dtg, const double* __restrict__ Ddg, double alpha, int accumulate) {
+  constexpr int n = N, m = MD, d = DIM, nz = DIM == 3 ? N : 1, mz = DIM == 3 ? MD : 1;
+  constexpr int np1 = n * n * nz, npd = m * m * mz;
+  extern __shared__ double sm[];
+  double* sI = sm; double* sIt = sI + m * n; double* sDd = sIt + m * n;
+  double* AC = sDd + m * m; double* UF = AC + 3 * npd; double* W1 = UF + npd; double* W2 = W1 + npd; double* CF = W2 + npd;
+  const size_t e = blockIdx.x;
+  load_mat_t(sI, I1dg, m * n); load_mat_t(sIt, I1dtg, m * n); load_mat_t(sDd, Ddg, m * m);
+  for (int i = threadIdx.x; i < d * npd; i += blockDim.x) AC[i] = 0.0;
+  __syncthreads();
+  const double* rx = rxd + e * (size_t)(d * d) * npd;
+#pragma unroll 1
+  for (int j = 0; j < d; ++j) {
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const double* src = (pass == 0 ? cf.p[j] : U.p[j]) + e * np1;
+      double* dst = pass == 0 ? CF : UF;
+      for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = src[i];
+      __syncthreads();
+      if constexpr (DIM == 2) { contract_t<m, n, 0, false, n, n, 1>(W2, W1, sI); contract_t<m, n, 1, false, m, n, 1>(dst, W2, sI); }
+      else { contract_t<m, n, 0, false, n, n, n>(W2, W1, sI); contract_t<m, n, 1, false, m, n, n>(W1, W2, sI); contract_t<m, n, 2, false, m, m, n>(dst, W1, sI); }
+    }
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+      if (k == 0) contract_t<m, m, 0, false, m, m, mz>(W1, UF, sDd);
+      else if (k == 1) contract_t<m, m, 1, false, m, m, mz>(W1, UF, sDd);
+      else contract_t<m, m, 2, false, m, m, mz>(W1, UF, sDd);
+      for (int i = threadIdx.x; i < npd; i += blockDim.x) {
+        double g = CF[i] * W1[i];
+#pragma unroll
+        for (int c = 0; c < d; ++c) AC[c * npd + i] += rx[(k * d + c) * npd + i] * g;
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < d; ++c) {
+    if constexpr (DIM == 2) { contract_t<n, m, 0, false, m, m, 1>(W1, AC + c * npd, sIt); contract_t<n, m, 1, false, n, m, 1>(W2, W1, sIt); }
+    else { contract_t<n, m, 0, false, m, m, m>(W1, AC + c * npd, sIt); contract_t<n, m, 1, false, n, m, m>(UF, W1, sIt); contract_t<n, m, 2, false, n, n, m>(W2, UF, sIt); }
+    double* of = out.p[c] + e * np1;
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[i];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K10 Schwarz FDM
+__device__ __forceinline__ int clamp_inner_t(int i, int n) { return i == 0 ? 1 : (i == n - 1 ? n - 2 : i); }
+template <int N, int DIM>
+__global__ void k_schwarz_fdm_t(const double* __restrict__ w, double* __restrict__ z, double* __restrict__ t, const double* __restrict__ S,
+                                const double* __restrict__ St, const double* __restrict__ dinv) {
+  constexpr int n = N, d = DIM, nz = DIM == 3 ? N : 1, np1 = n * n * nz, nn = n * n;
+  extern __shared__ double sm[];
+  double* sS = sm; double* sSt = sS + d * nn; double* A = sSt + d * nn; double* B = A + np1;
+  const size_t e = blockIdx.x;
+  load_mat_t(sS, S + e * (size_t)d * nn, d * nn); load_mat_t(sSt, St + e * (size_t)d * nn, d * nn);
+  for (int p = threadIdx.x; p < np1; p += blockDim.x) B[p] = w[e * np1 + p];
+  __syncthreads();
+  for (int p = threadIdx.x; p < np1; p += blockDim.x) {
+    int i = p % n, j = (p / n) % n, k = d == 3 ? p / nn : 1;
+    int nb = (i == 0 || i == n - 1) + (j == 0 || j == n - 1) + (d == 3 ? (k == 0 || k == n - 1) : 0);
+    double v = B[p];
+    if (nb == 1) { int ii = clamp_inner_t(i, n), jj = clamp_inner_t(j, n), kk = d == 3 ? clamp_inner_t(k, n) : 0; v -= B[(kk * n + jj) * n + ii]; }
+    A[p] = v;
+  }
+  __syncthreads();
+  double* res;
+  contract_t<n, n, 0, false, n, n, nz>(B, A, sSt);
+  contract_t<n, n, 1, false, n, n, nz>(A, B, sSt + nn);
+  if constexpr (DIM == 3) {
+    contract_t<n, n, 2, false, n, n, nz>(B, A, sSt + 2 * nn);
+    for (int p = threadIdx.x; p < np1; p += blockDim.x) B[p] *= dinv[e * np1 + p];
+    __syncthreads();
+    contract_t<n, n, 0, false, n, n, nz>(A, B, sS);
+    contract_t<n, n, 1, false, n, n, nz>(B, A, sS + nn);
+    contract_t<n, n, 2, false, n, n, nz>(A, B, sS + 2 * nn);
+    res = A;
+  } else {
+    for (int p = threadIdx.x; p < np1; p += blockDim.x) A[p] *= dinv[e * np1 + p];
+    __syncthreads();
+    contract_t<n, n, 0, false, n, n, nz>(B, A, sS);
+    contract_t<n, n, 1, false, n, n, nz>(A, B, sS + nn);
+    res = A;
+  }
+  for (int p = threadIdx.x; p < np1; p += blockDim.x) {
+    int i = p % n, j = (p / n) % n, k = d == 3 ? p / nn : 1;
+    int nb = (i == 0 || i == n - 1) + (j == 0 || j == n - 1) + (d == 3 ? (k == 0 || k == n - 1) : 0);
+    double v = res[p];
+    z[e * np1 + p] = v;
+    t[e * np1 + p] = nb == 1 ? v : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dispatch
+#define TP_CASE_N(N_) \
+  case N_ * 10 + 2: FN(N_, 2); break; \
+  case N_ * 10 + 3: FN(N_, 3); break;
+#define TP_SWITCH_N(key) switch (key) { TP_CASE_N(4) TP_CASE_N(5) TP_CASE_N(6) TP_CASE_N(7) TP_CASE_N(8) TP_CASE_N(9) TP_CASE_N(10) TP_CASE_N(11) TP_CASE_N(12) default: return false; }
+
+template <class K> static void set_smem(K kern, size_t smem) { if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
+
+bool tp_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, const double* in_mul, const double* out_mul, cudaStream_t st) {
+  size_t smem = (size_t)(2 * dm.q * dm.n + 7 * dm.np1) * sizeof(double);
+  if (smem > 220 * 1024) return false;
+  CPtr3 mk{{dm.mask[0], dm.mask[1], dm.mask[2]}};
+  int thr = tp_threads(dm.n, dm.ndim, dm.np1);
+#define FN(N_, D_) { static bool s_ = false; if (!s_) { set_smem(k_opdiv_t<N_, D_>, smem); s_ = true; } k_opdiv_t<N_, D_><<<(unsigned)dm.E, thr, smem, st>>>(u, p, dm.rxw2, dm.I12, dm.D12, scale, in_mul, mk, out_mul); }
+  TP_SWITCH_N(dm.n * 10 + dm.ndim)
+#undef FN
+  ++g_launches; return true;
+}
+bool tp_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st) {
+  size_t smem = (size_t)(2 * dm.q * dm.n + 7 * dm.np1) * sizeof(double);
+  if (smem > 220 * 1024) return false;
+  int thr = tp_threads(dm.n, dm.ndim, dm.np1);
+#define FN(N_, D_) { static bool s_ = false; if (!s_) { set_smem(k_opgradt_t<N_, D_>, smem); s_ = true; } k_opgradt_t<N_, D_><<<(unsigned)dm.E, thr, smem, st>>>(p, w, dm.rxw2, dm.I12t, dm.D12t); }
+  TP_SWITCH_N(dm.n * 10 + dm.ndim)
+#undef FN
+  ++g_launches; return true;
+}
+bool tp_schwarz_fdm(const DevMesh& dm, const double* w, double* z, double* t, cudaStream_t st) {
+  size_t smem = (size_t)(2 * dm.ndim * dm.n * dm.n + 2 * dm.np1) * sizeof(double);
+  int thr = tp_threads(dm.n, dm.ndim, dm.np1);
+#define FN(N_, D_) { static bool s_ = false; if (!s_) { set_smem(k_schwarz_fdm_t<N_, D_>, smem); s_ = true; } k_schwarz_fdm_t<N_, D_><<<(unsigned)dm.E, thr, smem, st>>>(w, z, t, dm.fdmS, dm.fdmSt, dm.fdmDinv); }
+  TP_SWITCH_N(dm.n * 10 + dm.ndim)
+#undef FN
+  ++g_launches; return true;
+}
+
+#define TP_CASE_NM(N_, M_) \
+  case (N_ * 100 + M_) * 10 + 2: FN(N_, M_, 2); break; \
+  case (N_ * 100 + M_) * 10 + 3: FN(N_, M_, 3); break;
+#define TP_SWITCH_NM(key) switch (key) { TP_CASE_NM(4, 6) TP_CASE_NM(5, 8) TP_CASE_NM(6, 9) TP_CASE_NM(7, 11) TP_CASE_NM(8, 12) TP_CASE_NM(9, 14) TP_CASE_NM(10, 15) TP_CASE_NM(12, 18) default: return false; }
+
+bool tp_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double alpha, int accumulate, cudaStream_t st) {
+  size_t smem = (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * dm.npd) * sizeof(double);
+  if (smem > 220 * 1024) return false;
+  int thr = tp_threads(dm.m, dm.ndim, dm.npd);
+#define FN(N_, M_, D_) { static bool s_ = false; if (!s_) { set_smem(k_convect_t<N_, M_, D_>, smem); s_ = true; } k_convect_t<N_, M_, D_><<<(unsigned)dm.E, thr, smem, st>>>(u, nf, C, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, alpha, accumulate); }
+  TP_SWITCH_NM((dm.n * 100 + dm.m) * 10 + dm.ndim)
+#undef FN
+  ++g_launches; return true;
+}
+bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st) {
+  size_t smem = (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * dm.npd) * sizeof(double);
+  if (smem > 220 * 1024) return false;
+  int thr = tp_threads(dm.m, dm.ndim, dm.npd);
+#define FN(N_, M_, D_) { static bool s_ = false; if (!s_) { set_smem(k_convect_adj_t<N_, M_, D_>, smem); s_ = true; } k_convect_adj_t<N_, M_, D_><<<(unsigned)dm.E, thr, smem, st>>>(U, c, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, alpha, accumulate); }
+  TP_SWITCH_NM((dm.n * 100 + dm.m) * 10 + dm.ndim)
+#undef FN
+  ++g_launches; return true;
+}
+
+}  // namespace nlk
