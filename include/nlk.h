@@ -104,6 +104,7 @@ int nlk_params_default(nlk_params* p);
 int nlk_ctx_create(const nlk_mesh* m, const nlk_params* p, int32_t device, nlk_ctx** out);
 int nlk_ctx_destroy(nlk_ctx* c);
 int nlk_ctx_set_tol(nlk_ctx* c, double vtol, double ptol);           /* setup_nek vtol/ptol args */
+int nlk_ctx_set_dt(nlk_ctx* c, double dt);                           /* Nek `dt` (param(12)) used when the base flow is zero: setup_nek disables recompute_dt (:79-83) */
 /* multi-rank: attach an NCCL communicator built from a broadcast unique id (128 bytes) */
 int nlk_comm_unique_id(char id[128]);
 int nlk_ctx_comm_init(nlk_ctx* c, const char id[128], int32_t rank, int32_t nranks);

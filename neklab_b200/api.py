@@ -53,7 +53,7 @@ EIGS_CB = C.CFUNCTYPE(None, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINT
 # every symbol include/nlk.h declares (checked by tests/test_cabi.py)
 SYMBOLS = """nlk_last_error nlk_version nlk_partition nlk_mesh_create nlk_mesh_destroy nlk_mesh_info nlk_mesh_glo_num
 nlk_mesh_field nlk_mesh_neighbor nlk_mesh_basis nlk_dense_eig nlk_params_default nlk_ctx_create nlk_ctx_destroy nlk_ctx_set_tol
-nlk_comm_unique_id nlk_ctx_comm_init nlk_ctx_sync nlk_ctx_stream nlk_vec_create nlk_vec_destroy nlk_vec_copy nlk_vec_zero
+nlk_ctx_set_dt nlk_comm_unique_id nlk_ctx_comm_init nlk_ctx_sync nlk_ctx_stream nlk_vec_create nlk_vec_destroy nlk_vec_copy nlk_vec_zero
 nlk_vec_rand nlk_vec_scal nlk_vec_axpby nlk_vec_dot nlk_vec_norm nlk_vec_size nlk_vec_save_rst nlk_vec_get_rst nlk_vec_nrst
 nlk_vec_clear_rst nlk_vec_upload nlk_vec_download nlk_basis_innerprod nlk_basis_axpy nlk_basis_dgs nlk_exptA_create
 nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_ctx_set_forcing
@@ -196,6 +196,9 @@ class Context:
 
     def set_tol(self, vtol, ptol):
         _chk(lib().nlk_ctx_set_tol(self.h, C.c_double(vtol), C.c_double(ptol)))
+
+    def set_dt(self, dt):
+        _chk(lib().nlk_ctx_set_dt(self.h, C.c_double(dt)))
 
     def sync(self):
         _chk(lib().nlk_ctx_sync(self.h))

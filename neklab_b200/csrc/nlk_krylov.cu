@@ -286,6 +286,7 @@ int nlk_svds(nlk_op* op, int32_t nsv, int32_t kdim, double tol, const nlk_vec* x
       res[j] = sv[j] > 0 ? std::fabs(beta[k + 1] * alpha[k] * vlast / sv[j]) : 0.0;
     }
     conv = 0; for (int j = 0; j < n; ++j) if (res[j] < tol) ++conv;
+    if (getenv("NLK_DEBUG_SVDS")) { printf("svds k=%d alpha=%.6e beta=%.6e :", k, alpha[k], beta[k + 1]); for (int j = 0; j < n; ++j) printf(" (%.6e, %.2e)", sv[j], res[j]); printf("\n"); }
     if (n >= nsv && conv >= nsv) { ++k; break; }
   }
   const int n = std::min(k, kdim);
@@ -313,12 +314,13 @@ int nlk_gmres(nlk_op* op, int32_t minus_identity, const nlk_vec* b, nlk_vec* x, 
   double bnorm; if (nlk_vec_norm(b, &bnorm)) return 1;
   const double tol = atol + rtol * bnorm;
   *info = 1;
-  for (int outer = 0; outer < maxiter; ++outer) {
+  for (int outer = 0; outer <= maxiter; ++outer) {
     if (apply(x, r)) return 1;
     if (nlk_vec_axpby(1.0, b, -1.0, r)) return 1;               // r = b - A x
     r->nrst = 0;
     double beta; if (nlk_vec_norm(r, &beta)) return 1;
     if (beta < tol) { *info = 0; break; }
+    if (outer == maxiter) break;
     if (nlk_vec_copy(V[0], r)) return 1; if (nlk_vec_scal(V[0], 1.0 / beta)) return 1;
     std::vector<double> H((size_t)(kdim + 1) * kdim, 0.0), cs(kdim), sn(kdim), g(kdim + 1, 0.0), y(kdim);
     g[0] = beta; int kk = 0;

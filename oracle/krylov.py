@@ -132,35 +132,41 @@ def eigs(apply, x0, nev, kdim, tol=RTOL_DP, maxiter=10, log=None):
 
 
 def svds(A, x0, nsv, kdim, tol=RTOL_DP):
-    """Golub-Kahan bidiagonalisation (LightKrylov `svds`): matvec + rmatvec + DGS per step."""
+    """Golub-Kahan bidiagonalisation (LightKrylov `svds`): per step one matvec + one rmatvec + DGS against U and V.
+
+    A V_k = U_k B_k (B_k upper bidiagonal: diag alpha, superdiag beta), A^T U_k = V_k B_k^T + beta_k v_{k+1} e_k^T;
+    residual of triplet i = |beta_k| * |last component of the left singular vector of B_k|.
+    Returns (sigma descending, residuals, U, V, k).
+    """
     U, V = [], []
     v = x0.copy(); v.scal(1.0 / v.norm())
     V.append(v)
-    Bm = np.zeros((kdim + 1, kdim))
+    alpha, beta = [], []
     sig = res = None
+    k = 0
     for k in range(kdim):
         u = A.matvec(V[k])
-        if k > 0:
-            u.axpby(-Bm[k - 1, k], U[k - 1], 1.0) if False else None
         if U:
             double_gram_schmidt_step(u, U)
-        alpha = u.norm(); u.scal(1.0 / alpha)
-        U.append(u); Bm[k, k] = alpha
+        a = u.norm(); u.scal(1.0 / a)
+        U.append(u); alpha.append(a)
         w = A.rmatvec(u)
         double_gram_schmidt_step(w, V)
-        beta = w.norm(); w.scal(1.0 / beta)
-        V.append(w); Bm[k + 1, k] = beta if k + 1 <= kdim else 0.0
-        # B is lower-bidiagonal in this (U,V) convention: A V_k = U_k B_k^T ... use SVD of the k x k block
-        Bk = np.zeros((k + 1, k + 1))
-        for i in range(k + 1):
-            Bk[i, i] = Bm[i, i]
-            if i + 1 <= k:
-                Bk[i, i + 1] = Bm[i + 1, i]
-        uu, sig, vt = np.linalg.svd(Bk)
-        res = np.abs(beta * uu[k, :])
-        if int((res[:nsv] < tol).sum()) >= nsv and k + 1 >= nsv:
+        b = w.norm()
+        if b > ATOL_DP:
+            w.scal(1.0 / b)
+        V.append(w); beta.append(b)
+        n = k + 1
+        B = np.zeros((n, n))
+        for i in range(n):
+            B[i, i] = alpha[i]
+            if i + 1 < n:
+                B[i, i + 1] = beta[i]
+        P, sig, Qt = np.linalg.svd(B)
+        res = np.abs(b * P[n - 1, :])
+        if n >= nsv and int((res < tol).sum()) >= nsv:
             break
-    return sig, res, U, V
+    return sig, res, U, V, k + 1
 
 
 def gmres(apply, b, x0, kdim=30, atol=ATOL_DP, rtol=RTOL_DP, maxiter=10):

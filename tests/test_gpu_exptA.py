@@ -118,3 +118,41 @@ def test_vector_semantics(setup):
     ro = a.get_rst(1)
     assert rel(rv[1], ro.v[1]) < 1e-14 and rel(rp, ro.pr) < 1e-14
     ad.zero(); assert ad.nrst == 0 and ad.norm() == 0.0
+
+
+# ----------------------------------------------------------------------------------------------- exptA_temp_linop
+def test_boussinesq_filter_parity(nlk_lib):
+    """exptA_temp_linop path (src/linops/exponential_propagator_temp.f90; rayBen config): velocity + temperature,
+    Boussinesq forcing through the declarative body force, explicit modal filter (q_filter)."""
+    from neklab_b200 import api
+    cbt = None
+    om, bm, _ = box_case(ndim=2, nel=(5, 3), n=8, lxd=12, periodic=[True, False], hi=(4.0, 1.0), warp=False)
+    cbc_t = om.cbc_v.copy(); cbc_t[cbc_t == "W  "] = "t  "
+    from oracle.mesh import SEMesh
+    om = SEMesh(om.coords, om.vertex, om.cbc_v, 12, cbc_t=cbc_t)
+    kw = dict(viscosity=1.0, torder=3, vtol=1e-13, ptol=1e-13, ttol=1e-13, ifheat=True, conductivity=1.0, rhocp=1.0,
+              buoyancy=(0.0, 1900.0, 0.0), filter_weight=0.01, filter_cutoff=0.84, gmres_maxit=2000, cg_maxit=2000)
+    prm = StepParams(**kw)
+    st = PertStepper(om, prm, precond=SchwarzCoarse(om))
+    bf = NekVec(om, 3, ifheat=True)
+    bf.theta = 1.0 - om.coords[:, 1]                       # conduction state (rayBen.usr userbc: temp = 1 - y)
+    st.dt = 0.004                                          # zero base flow: dt is preset (setup_nek: recompute_dt disabled)
+    A_or = ExptA(st, 0.02, bf)
+    x0 = seeded_field(om, 21, ifheat=True)
+    y_or = A_or.matvec(x0)
+    m = api.Mesh(om.coords, om.vertex, om.cbc_v, 12, cbc_t=cbc_t)
+    kw2 = dict(kw); kw2["ifheat"] = 1
+    ctx = api.Context(m, api.default_params(**kw2))
+    bd = ctx.vec(); bd.upload(bf.v, bf.pr, bf.theta)
+    xd = ctx.vec(); xd.upload(x0.v, x0.pr, x0.theta)
+    A = api.exptA_linop(ctx, 0.02, bd)
+    api.lib().nlk_ctx_set_dt(ctx.h, __import__("ctypes").c_double(0.004))
+    yd = A.matvec(xd)
+    v, pr, th = yd.download()
+    assert A.stats()["nsteps"] == st.nsteps == 5
+    err_v = _wnorm(om, [v[c] - y_or.v[c] for c in range(2)]) / _wnorm(om, y_or.v)
+    err_t = _wnorm(om, [th - y_or.theta]) / _wnorm(om, [y_or.theta])
+    assert err_v < TOL_APPLY and err_t < TOL_APPLY, (err_v, err_t)
+    assert yd.get_size() == y_or.size()
+    assert abs(yd.dot(yd) - y_or.dot(y_or)) < 1e-9 * y_or.dot(y_or)      # theta enters the inner product
+    ctx.close()

@@ -1,0 +1,111 @@
+"""GPU parity of the Krylov drivers (eigs / svds / gmres / block Gram-Schmidt) against the oracle's LightKrylov
+restatement, on the same operator and the same start vector."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.krylov import double_gram_schmidt_step, eigs as eigs_or, gmres as gmres_or, svds as svds_or
+from oracle.precond import SchwarzCoarse
+from oracle.stepper import ExptA, NekVec, PertStepper, StepParams, seeded_field
+from tests.util import GOLDEN, box_case, cylinder_case, nlk_mesh, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small(nlk_lib):
+    from neklab_b200 import api
+    om, _, _ = box_case(ndim=2, nel=(4, 3), n=6, lxd=9, bc={"xlo": "v  ", "xhi": "O  "})
+    x = om.coords
+    bf = NekVec(om, 3)
+    bf.v = [1.0 + 0.3 * np.sin(0.5 * x[:, 1]), 0.2 * np.cos(0.4 * x[:, 0])]
+    kw = dict(viscosity=0.05, torder=3, vtol=1e-13, ptol=1e-13, gmres_maxit=2000, cg_maxit=2000)
+    A_or = ExptA(PertStepper(om, StepParams(**kw), precond=SchwarzCoarse(om)), 0.2, bf)
+    ctx = api.Context(nlk_mesh(om), api.default_params(**kw))
+    bd = ctx.vec(); bd.upload(bf.v, bf.pr)
+    A = api.exptA_linop(ctx, 0.2, bd)
+    yield om, ctx, A_or, A
+    ctx.close()
+
+
+def _dev(ctx, nv):
+    d = ctx.vec(); d.upload(nv.v, nv.pr, nv.theta); return d
+
+
+def test_block_gram_schmidt(small):
+    import ctypes as C
+    from neklab_b200 import api
+    om, ctx, A_or, A = small
+    X = [seeded_field(om, s) for s in range(5)]
+    y = seeded_field(om, 99)
+    Xd = [_dev(ctx, x) for x in X]; yd = _dev(ctx, y)
+    arr = (C.c_void_p * len(Xd))(*[x.h for x in Xd])
+    h = np.zeros(len(X)); nrm = C.c_double()
+    api._chk(api.lib().nlk_basis_dgs(yd.h, arr, C.c_int32(len(X)), api._p(h), C.byref(nrm)))
+    h_or = double_gram_schmidt_step(y, X)
+    assert rel(h, h_or) < 1e-12
+    assert abs(nrm.value - y.norm()) < 1e-12 * y.norm()
+    v, _, _ = yd.download()
+    assert rel(v[0], y.v[0]) < 1e-12
+
+
+def test_eigs_matches_oracle(small):
+    from neklab_b200 import api
+    om, ctx, A_or, A = small
+    x0 = seeded_field(om, 7)
+    # kdim large enough that no Krylov-Schur restart happens: the restart bases (Schur vectors in the oracle, an orthonormal
+    # basis of the same invariant subspace here) differ, and the rst arithmetic makes the operator history-dependent
+    lam_or, res_or, *_ = eigs_or(A_or.matvec, x0, nev=2, kdim=60, tol=1e-7, maxiter=1)
+    r = api.eigs(A, nev=2, kdim=60, tol=1e-7, x0=_dev(ctx, x0))
+    assert r["info"] == 0
+    # north_star: leading eigenvalues within 1e-8 relative
+    assert abs(abs(r["lam"][0]) - abs(lam_or[0])) < 1e-8 * abs(lam_or[0])
+    assert abs(r["lam"][0].real - lam_or[0].real) < 1e-8 and abs(abs(r["lam"][0].imag) - abs(lam_or[0].imag)) < 1e-8
+
+
+def test_svds_matches_oracle(small):
+    import ctypes as C
+    from neklab_b200 import api
+    om, ctx, A_or, A = small
+    x0 = seeded_field(om, 8)
+    sig_or, res_or, _, _, k_or = svds_or(A_or, x0, nsv=2, kdim=10, tol=1e-6)
+    sig = np.zeros(2); res = np.zeros(2); nit = C.c_int32(); info = C.c_int32()
+    xd = _dev(ctx, x0)                                      # keep the handle alive across the call
+    api._chk(api.lib().nlk_svds(A.h, C.c_int32(2), C.c_int32(10), C.c_double(1e-6), xd.h, api._p(sig), api._p(res), None, None, C.byref(nit), C.byref(info)))
+    assert nit.value == k_or
+    assert rel(sig, sig_or[:2]) < 1e-8
+    assert rel(res, res_or[:2]) < 1e-5
+
+
+def test_gmres_fixed_point_jacobian(small):
+    """nek_jacobian%matvec = exptA - I (src/systems/fixed_point.f90:42-96) solved with restarted GMRES."""
+    import ctypes as C
+    from neklab_b200 import api
+    om, ctx, A_or, A = small
+    b = seeded_field(om, 9)
+    bd = _dev(ctx, b); xd = ctx.vec(); xd.zero()
+    info = C.c_int32()
+    api._chk(api.lib().nlk_gmres(A.h, C.c_int32(1), bd.h, xd.h, C.c_int32(20), C.c_double(1e-10), C.c_double(1e-8), C.c_int32(25), C.c_int32(0), C.byref(info)))
+    assert info.value == 0
+    # residual check with the device operator
+    r = A.matvec(xd); r.axpby(-1.0, xd, 1.0); r.axpby(1.0, bd, -1.0)
+    assert r.norm() < 1e-6 * bd.norm()
+
+
+def test_cylinder_eigs_same_start_vector_as_oracle_golden(nlk_lib):
+    """Cylinder Re=50, kdim 128: same start vector and restart-field arithmetic as the committed oracle run
+    (tests/golden/cylinder_eig_oracle.json, sparse-direct inner solves) -> leading modulus within 1e-8 relative needs the
+    inner tolerances tightened; with the reference tolerances (1e-9/1e-7) 1e-6 is asserted."""
+    from neklab_b200 import api
+    om, bf, prm, z = cylinder_case()
+    gold = json.load(open(os.path.join(GOLDEN, "cylinder_eig_oracle.json")))
+    ctx = api.Context(nlk_mesh(om), api.default_params(viscosity=1 / 50.0, torder=3, vtol=1e-11, ptol=1e-10, gmres_maxit=400, pr_proj=20))
+    bd = ctx.vec(); bd.upload(bf.v, bf.pr)
+    A = api.exptA_linop(ctx, 1.0, bd)
+    x0 = seeded_field(om, gold["seed"], torder=3)
+    r = api.eigs(A, nev=2, kdim=128, x0=_dev(ctx, x0))
+    ctx.close()
+    assert r["info"] == 0
+    assert abs(abs(r["lam"][0]) - gold["modulus"][0]) < 1e-6 * gold["modulus"][0], (abs(r["lam"][0]), gold["modulus"][0])
