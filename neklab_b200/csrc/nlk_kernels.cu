@@ -9,6 +9,14 @@ thread_local long g_launches = 0;
 #define LAUNCH_COUNT() (++g_launches)
 
 static inline int cdiv(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+// 4-way unrolled grid-stride loop: four independent (predicated) iterations per trip keep >= 4x the loads in flight
+#define NLK_STREAM4_BEGIN(i, n)                                                                                        \
+  for (size_t base_ = (size_t)blockIdx.x * blockDim.x * 4 + threadIdx.x; base_ < (n); base_ += (size_t)gridDim.x * blockDim.x * 4) { \
+    _Pragma("unroll") for (int u_ = 0; u_ < 4; ++u_) {                                                                \
+      const size_t i = base_ + (size_t)u_ * blockDim.x;                                                               \
+      if (i < (n)) {
+#define NLK_STREAM4_END }}}
+static inline int stream_grid(size_t n, int cap) { int g = (int)((n + 1023) / 1024); return g < 1 ? 1 : (g > cap ? cap : g); }
 static const int RED_BLOCKS = 1184;  // 148 SMs x 8
 static const int RED_THREADS = 256;
 
@@ -75,10 +83,19 @@ __device__ bool grid_reduce(double (&v)[NV], Reducer red) {
 }
 
 // ------------------------------------------------------------------------------------------------ K1 axhelm
+// GLL derivative matrix in constant memory for the warp-uniform accesses of the t-direction (k is a compile-time loop
+// index): constant-cache broadcasts instead of shared-memory wavefronts (ncu r01: the LSU/shared pipe was the limiter).
+__constant__ double c_D[16 * 16];
+static int c_D_n = -1;
+static void ensure_const_D(const DevMesh& dm, cudaStream_t st) {
+  if (c_D_n == dm.n) return;
+  cudaMemcpyToSymbolAsync(c_D, dm.D, sizeof(double) * dm.n * dm.n, 0, cudaMemcpyDeviceToDevice, st);
+  c_D_n = dm.n;
+}
 // One element per (threadIdx.y) slice; thread (i,j) owns the k-column of the element (register-tiled k-loop, 3-D).
 // FUSE_CG: the CG search-direction update p = r/(h1*diagA+h2*diagB) + beta*p is applied while loading.
 template <int N, int DIM, bool FUSE_CG>
-__global__ void __launch_bounds__(N * N * (N * N >= 100 ? 1 : (N * N >= 64 ? 2 : 4)))
+__global__ void __launch_bounds__(N * N * (N * N >= 100 ? 1 : (N * N >= 64 ? 2 : 4)), (N == 8 ? 8 : 1))
 k_axhelm(const double* __restrict__ u, double* __restrict__ pio, const double* __restrict__ r, double* __restrict__ w,
          const double* __restrict__ G, const double* __restrict__ bm1, const double* __restrict__ Dg,
          const double* __restrict__ diagA, const double* __restrict__ diagB, double h1, double h2,
@@ -114,9 +131,21 @@ k_axhelm(const double* __restrict__ u, double* __restrict__ pio, const double* _
   }
 #pragma unroll
   for (int k = 0; k < NZ; ++k) rw[k] = 0.0;
+  // geometric factors of slice k are fetched one iteration ahead (software prefetch: more HBM bytes in flight per warp)
+  const double* Ge = G + (size_t)(active ? e : 0) * NG * NP + tid;
+  double gn[NG];
+#pragma unroll
+  for (int c = 0; c < NG; ++c) gn[c] = Ge[c * NP];
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < NZ; ++k) {
+    double gc[NG];
+#pragma unroll
+    for (int c = 0; c < NG; ++c) gc[c] = gn[c];
+    if (k + 1 < NZ) {
+#pragma unroll
+      for (int c = 0; c < NG; ++c) gn[c] = Ge[c * NP + (k + 1) * NN];
+    }
     s_u[le][tid] = ru[k];
     __syncthreads();
     double ur = 0, us = 0, ut = 0;
@@ -127,19 +156,16 @@ k_axhelm(const double* __restrict__ u, double* __restrict__ pio, const double* _
     }
     if (DIM == 3) {
 #pragma unroll
-      for (int l = 0; l < N; ++l) ut += sD[k * N + l] * ru[l];
+      for (int l = 0; l < N; ++l) ut += c_D[k * N + l] * ru[l];
     }
-    const size_t gb = (size_t)(active ? e : 0) * NG * NP + k * NN + tid;
     double gr, gs, gt = 0;
     if (DIM == 3) {
-      double g11 = G[gb], g22 = G[gb + NP], g33 = G[gb + 2 * NP], g12 = G[gb + 3 * NP], g13 = G[gb + 4 * NP], g23 = G[gb + 5 * NP];
-      gr = g11 * ur + g12 * us + g13 * ut;
-      gs = g12 * ur + g22 * us + g23 * ut;
-      gt = g13 * ur + g23 * us + g33 * ut;
+      gr = gc[0] * ur + gc[3] * us + gc[4] * ut;
+      gs = gc[3] * ur + gc[1] * us + gc[5] * ut;
+      gt = gc[4] * ur + gc[5] * us + gc[2] * ut;
     } else {
-      double g11 = G[gb], g22 = G[gb + NP], g12 = G[gb + 2 * NP];
-      gr = g11 * ur + g12 * us;
-      gs = g12 * ur + g22 * us;
+      gr = gc[0] * ur + gc[2] * us;
+      gs = gc[2] * ur + gc[1] * us;
     }
     s_gr[le][tid] = gr; s_gs[le][tid] = gs;
     __syncthreads();
@@ -149,7 +175,7 @@ k_axhelm(const double* __restrict__ u, double* __restrict__ pio, const double* _
     rw[k] += acc;
     if (DIM == 3) {
 #pragma unroll
-      for (int l = 0; l < N; ++l) rw[l] += sD[k * N + l] * gt;
+      for (int l = 0; l < N; ++l) rw[l] += c_D[k * N + l] * gt;
     }
     __syncthreads();
   }
@@ -163,6 +189,7 @@ template <int N, int DIM>
 static void axhelm_dispatch(const DevMesh& dm, const double* u, double* pio, const double* r, double* w, double h1, double h2,
                             const SolverScal* sc, bool fuse, cudaStream_t st) {
   constexpr int EPB = N * N >= 100 ? 1 : (N * N >= 64 ? 2 : 4);
+  ensure_const_D(dm, st);
   dim3 block(N * N, EPB), grid(cdiv(dm.E, EPB));
   if (fuse) k_axhelm<N, DIM, true><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, dm.diagA, dm.diagB, h1, h2, sc, dm.E);
   else k_axhelm<N, DIM, false><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, dm.diagA, dm.diagB, h1, h2, sc, dm.E);
@@ -231,8 +258,7 @@ void launch_unpack_add(double* u, const int32_t* off, const int32_t* idx, int cn
 // ------------------------------------------------------------------------------------------------ pointwise
 __global__ void k_lin(double* __restrict__ out, size_t n, double a0, const double* __restrict__ x0, double a1, const double* __restrict__ x1,
                       double a2, const double* __restrict__ x2, double a3, const double* __restrict__ x3, const double* __restrict__ mul) {
-#pragma unroll 4
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  NLK_STREAM4_BEGIN(i, n)
     double v = 0;
     if (x0) v += a0 * x0[i];
     if (x1) v += a1 * x1[i];
@@ -240,25 +266,24 @@ __global__ void k_lin(double* __restrict__ out, size_t n, double a0, const doubl
     if (x3) v += a3 * x3[i];
     if (mul) v *= mul[i];
     out[i] = v;
-  }
+    NLK_STREAM4_END
 }
 void launch_lin(double* out, size_t n, double a0, const double* x0, double a1, const double* x1, double a2, const double* x2, double a3,
                 const double* x3, const double* mul, cudaStream_t st) {
   if (!n) return;
-  int grid = std::min(cdiv(n, 256), 148 * 16);
+  int grid = stream_grid(n, 148 * 16);
   k_lin<<<grid, 256, 0, st>>>(out, n, a0, x0, a1, x1, a2, x2, a3, x3, mul); LAUNCH_COUNT();
 }
 __global__ void k_axpy_mm(double* __restrict__ out, size_t n, const double* __restrict__ x0, double a, const double* __restrict__ x1,
                           const double* __restrict__ m1, const double* __restrict__ m2) {
-#pragma unroll 4
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  NLK_STREAM4_BEGIN(i, n)
     double v = a * x1[i] * m1[i];
     if (m2) v *= m2[i];
     out[i] = (x0 ? x0[i] : 0.0) + v;
-  }
+    NLK_STREAM4_END
 }
 void launch_axpy_mm(double* out, size_t n, const double* x0, double a, const double* x1, const double* m1, const double* m2, cudaStream_t st) {
-  k_axpy_mm<<<std::min(cdiv(n, 256), 148 * 16), 256, 0, st>>>(out, n, x0, a, x1, m1, m2); LAUNCH_COUNT();
+  k_axpy_mm<<<stream_grid(n, 148 * 16), 256, 0, st>>>(out, n, x0, a, x1, m1, m2); LAUNCH_COUNT();
 }
 __global__ void k_fill(double* out, size_t n, double v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = v;
@@ -549,13 +574,12 @@ __global__ void k_rhs_tail(RhsTail t, size_t n, const double* __restrict__ bm1, 
   const int f = blockIdx.y;
   double* bf = t.bf[f]; double* e1 = t.e1[f]; double* e2 = t.e2[f]; const double* u = t.u[f]; double* l1 = t.lag1[f]; double* l2 = t.lag2[f];
   const double coef = t.coef[f];
-#pragma unroll 4
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  NLK_STREAM4_BEGIN(i, n)
     double b = bf[i], x1 = e1[i], x2 = e2[i], uu = u[i], a1 = l1[i], a2 = l2[i];
     e2[i] = x1; e1[i] = b;
     bf[i] = ab0 * b + ab1 * x1 + ab2 * x2 + coef * bm1[i] * (bd1 * uu + bd2 * a1 + bd3 * a2);
     l2[i] = a1; l1[i] = uu;
-  }
+    NLK_STREAM4_END
 }
 void launch_rhs_tail(const DevMesh& dm, const RhsTail& t, int nf, double ab0, double ab1, double ab2, double bd1, double bd2, double bd3,
                      cudaStream_t st) {
@@ -602,8 +626,7 @@ k_cg_update_reduce(double* __restrict__ x, double* __restrict__ r, const double*
   if (sc->done) return;
   const double alpha = first ? 0.0 : sc->alpha;
   double v[2] = {0.0, 0.0};
-#pragma unroll 4
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  NLK_STREAM4_BEGIN(i, n)
     double ri = r[i];
     if (!first) {
       x[i] += alpha * p[i];
@@ -614,7 +637,7 @@ k_cg_update_reduce(double* __restrict__ x, double* __restrict__ r, const double*
     double m = mult[i];
     v[0] += ri * z * m;
     v[1] += ri * ri * m * binv[i];
-  }
+    NLK_STREAM4_END
   if (grid_reduce<2>(v, red)) {
     sc->red[0] = v[0]; sc->red[1] = v[1];
     if (!defer) cg_finalize_zr(sc, vol);
@@ -622,7 +645,7 @@ k_cg_update_reduce(double* __restrict__ x, double* __restrict__ r, const double*
 }
 void launch_cg_update_reduce(const DevMesh& dm, double* x, double* r, const double* p, const double* w, const double* mask, double h1,
                              double h2, SolverScal* sc, Reducer red, int first, int defer, cudaStream_t st) {
-  int grid = std::min(cdiv(dm.N1, RED_THREADS), RED_BLOCKS);
+  int grid = stream_grid(dm.N1, RED_BLOCKS);
   k_cg_update_reduce<<<grid, RED_THREADS, 0, st>>>(x, r, p, w, mask, dm.diagA, dm.diagB, dm.vmult, dm.binvm1, h1, h2, dm.volvm1, dm.N1, sc, red, first, defer);
   LAUNCH_COUNT();
 }
@@ -635,25 +658,33 @@ k_cg_pap(const double* __restrict__ w, const double* __restrict__ p, const doubl
   if (grid_reduce<1>(v, red)) { sc->red[2] = v[0]; if (!defer) cg_finalize_pap(sc); }
 }
 void launch_cg_pap(const DevMesh& dm, const double* w, const double* p, const double* mask, SolverScal* sc, Reducer red, int defer, cudaStream_t st) {
-  int grid = std::min(cdiv(dm.N1, RED_THREADS), RED_BLOCKS);
+  int grid = stream_grid(dm.N1, RED_BLOCKS);
   k_cg_pap<<<grid, RED_THREADS, 0, st>>>(w, p, mask, dm.vmult, dm.N1, sc, red, defer); LAUNCH_COUNT();
 }
 
 // ------------------------------------------------------------------------------------------------ dots
+template <int NP, bool W>
 __global__ void __launch_bounds__(256)
-k_dot(size_t n, CPtr4 a, CPtr4 b, int npairs, const double* __restrict__ c, double* out, Reducer red) {
+k_dot(size_t n, const double* __restrict__ a0, const double* __restrict__ a1, const double* __restrict__ a2, const double* __restrict__ a3,
+      const double* __restrict__ b0, const double* __restrict__ b1, const double* __restrict__ b2, const double* __restrict__ b3,
+      const double* __restrict__ c, double* out, Reducer red) {
   double v[1] = {0.0};
-#pragma unroll 4
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    double s = 0;
-    for (int k = 0; k < npairs; ++k) s += a.p[k][i] * b.p[k][i];
-    v[0] += c ? s * c[i] : s;
-  }
+  NLK_STREAM4_BEGIN(i, n)
+    double s = a0[i] * b0[i];
+    if (NP > 1) s += a1[i] * b1[i];
+    if (NP > 2) s += a2[i] * b2[i];
+    if (NP > 3) s += a3[i] * b3[i];
+    v[0] += W ? s * c[i] : s;
+    NLK_STREAM4_END
   if (grid_reduce<1>(v, red)) out[0] = v[0];
 }
 void launch_dot(size_t n, CPtr4 a, CPtr4 b, int npairs, const double* c, double* out, Reducer red, cudaStream_t st) {
-  int grid = std::min(cdiv(n, RED_THREADS), RED_BLOCKS);
-  k_dot<<<grid, RED_THREADS, 0, st>>>(n, a, b, npairs, c, out, red); LAUNCH_COUNT();
+  int grid = stream_grid(n, RED_BLOCKS);
+#define NLK_DOT(NP_) { if (c) k_dot<NP_, true><<<grid, RED_THREADS, 0, st>>>(n, a.p[0], a.p[1], a.p[2], a.p[3], b.p[0], b.p[1], b.p[2], b.p[3], c, out, red); \
+                       else k_dot<NP_, false><<<grid, RED_THREADS, 0, st>>>(n, a.p[0], a.p[1], a.p[2], a.p[3], b.p[0], b.p[1], b.p[2], b.p[3], c, out, red); }
+  switch (npairs) { case 1: NLK_DOT(1) break; case 2: NLK_DOT(2) break; case 3: NLK_DOT(3) break; default: NLK_DOT(4) break; }
+#undef NLK_DOT
+  LAUNCH_COUNT();
 }
 
 // h[j] = sum_i V[j*ld + i] * w[i], j < k <= 32: w is streamed once for all k rows (tall-skinny V^T w).
@@ -663,30 +694,28 @@ k_multidot(const double* __restrict__ V, size_t ld, int k0, int k, const double*
   double v[KB];
 #pragma unroll
   for (int j = 0; j < KB; ++j) v[j] = 0.0;
-#pragma unroll 4
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  NLK_STREAM4_BEGIN(i, n)
     double wi = w[i];
 #pragma unroll
     for (int j = 0; j < KB; ++j) if (k0 + j < k) v[j] += V[(size_t)(k0 + j) * ld + i] * wi;
-  }
+    NLK_STREAM4_END
   if (grid_reduce<KB>(v, red)) {
     for (int j = 0; j < KB; ++j) if (k0 + j < k) h[k0 + j] = v[j];
   }
 }
 void launch_multidot(const double* V, size_t ld, int k, const double* w, size_t n, double* h, Reducer red, cudaStream_t st) {
-  int grid = std::min(cdiv(n, RED_THREADS), RED_BLOCKS);
+  int grid = stream_grid(n, RED_BLOCKS);
   for (int k0 = 0; k0 < k; k0 += 8) { k_multidot<8><<<grid, RED_THREADS, 0, st>>>(V, ld, k0, k, w, n, h, red); LAUNCH_COUNT(); }
 }
 __global__ void k_multiaxpy(double* __restrict__ w, const double* __restrict__ V, size_t ld, int k, const double* __restrict__ h, double sign, size_t n) {
   extern __shared__ double sh[];
   for (int j = threadIdx.x; j < k; j += blockDim.x) sh[j] = sign * h[j];
   __syncthreads();
-#pragma unroll 4
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  NLK_STREAM4_BEGIN(i, n)
     double s = w[i];
     for (int j = 0; j < k; ++j) s += sh[j] * V[(size_t)j * ld + i];
     w[i] = s;
-  }
+    NLK_STREAM4_END
 }
 // w += sign * V h, and out[0] = sum_i w_i^2 of the result (one pass)
 __global__ void __launch_bounds__(256)
@@ -696,16 +725,15 @@ k_multiaxpy_norm(double* __restrict__ w, const double* __restrict__ V, size_t ld
   for (int j = threadIdx.x; j < k; j += blockDim.x) sh[j] = sign * h[j];
   __syncthreads();
   double v[1] = {0.0};
-#pragma unroll 4
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  NLK_STREAM4_BEGIN(i, n)
     double s = w[i];
     for (int j = 0; j < k; ++j) s += sh[j] * V[(size_t)j * ld + i];
     w[i] = s; v[0] += s * s;
-  }
+    NLK_STREAM4_END
   if (grid_reduce<1>(v, red)) out[0] = v[0];
 }
 void launch_multiaxpy_norm(double* w, const double* V, size_t ld, int k, const double* h, double sign, size_t n, double* out, Reducer red, cudaStream_t st) {
-  int grid = std::min(cdiv(n, RED_THREADS), RED_BLOCKS);
+  int grid = stream_grid(n, RED_BLOCKS);
   k_multiaxpy_norm<<<grid, RED_THREADS, (k > 0 ? k : 1) * sizeof(double), st>>>(w, V, ld, k, h, sign, n, out, red); LAUNCH_COUNT();
 }
 // out = in * rsqrt(*s)  (zero if *s <= 0): normalisation with a device-resident scalar
@@ -718,7 +746,7 @@ void launch_scale_rsqrt(double* out, const double* in, size_t n, const double* s
 }
 void launch_multiaxpy(double* w, const double* V, size_t ld, int k, const double* h, double sign, size_t n, cudaStream_t st) {
   if (k <= 0) return;
-  k_multiaxpy<<<std::min(cdiv(n, 256), 148 * 8), 256, k * sizeof(double), st>>>(w, V, ld, k, h, sign, n); LAUNCH_COUNT();
+  k_multiaxpy<<<stream_grid(n, 148 * 8), 256, k * sizeof(double), st>>>(w, V, ld, k, h, sign, n); LAUNCH_COUNT();
 }
 
 // ------------------------------------------------------------------------------------------------ K10 Schwarz
