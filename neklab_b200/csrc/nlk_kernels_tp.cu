@@ -7,7 +7,36 @@
 
 namespace nlk {
 
-template <int MO, int MI, int DIR, bool ACC, int N0, int N1, int N2>
+// 1-D operators of the current (lx1, lxd) in constant memory: with fully unrolled (o, l) the matrix entry becomes a
+// constant-bank operand of the DFMA instead of a shared-memory broadcast load (ncu r01: LSU/shared pipe was the limiter).
+enum { MAT_SMEM = -1, MAT_I12 = 0, MAT_D12, MAT_I12T, MAT_D12T, MAT_I1D, MAT_I1DT, MAT_DD };
+__constant__ double c_I12[16 * 16], c_D12[16 * 16], c_I12T[16 * 16], c_D12T[16 * 16], c_I1D[24 * 16], c_I1DT[24 * 16], c_DD[24 * 24];
+static int c_ops_n = -1, c_ops_m = -1;
+static void ensure_const_ops(const DevMesh& dm, cudaStream_t st) {
+  if (c_ops_n == dm.n && c_ops_m == dm.m) return;
+  const size_t qn = sizeof(double) * dm.q * dm.n, mn = sizeof(double) * dm.m * dm.n, mm = sizeof(double) * dm.m * dm.m;
+  cudaMemcpyToSymbolAsync(c_I12, dm.I12, qn, 0, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyToSymbolAsync(c_D12, dm.D12, qn, 0, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyToSymbolAsync(c_I12T, dm.I12t, qn, 0, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyToSymbolAsync(c_D12T, dm.D12t, qn, 0, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyToSymbolAsync(c_I1D, dm.I1d, mn, 0, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyToSymbolAsync(c_I1DT, dm.I1dt, mn, 0, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyToSymbolAsync(c_DD, dm.Dd, mm, 0, cudaMemcpyDeviceToDevice, st);
+  c_ops_n = dm.n; c_ops_m = dm.m;
+}
+template <int MAT>
+__device__ __forceinline__ double mat_at(const double* __restrict__ M, int idx) {
+  if constexpr (MAT == MAT_I12) return c_I12[idx];
+  else if constexpr (MAT == MAT_D12) return c_D12[idx];
+  else if constexpr (MAT == MAT_I12T) return c_I12T[idx];
+  else if constexpr (MAT == MAT_D12T) return c_D12T[idx];
+  else if constexpr (MAT == MAT_I1D) return c_I1D[idx];
+  else if constexpr (MAT == MAT_I1DT) return c_I1DT[idx];
+  else if constexpr (MAT == MAT_DD) return c_DD[idx];
+  else return M[idx];
+}
+
+template <int MO, int MI, int DIR, bool ACC, int N0, int N1, int N2, int MAT = MAT_SMEM>
 __device__ __forceinline__ void contract_t(double* __restrict__ out, const double* __restrict__ in, const double* __restrict__ M) {
   constexpr int O0 = DIR == 0 ? MO : N0, O1 = DIR == 1 ? MO : N1, O2 = DIR == 2 ? MO : N2;
   constexpr int P0 = DIR == 0 ? 1 : N0, P1 = DIR == 1 ? 1 : N1, P2 = DIR == 2 ? 1 : N2;
@@ -25,7 +54,7 @@ __device__ __forceinline__ void contract_t(double* __restrict__ out, const doubl
       for (int o = 0; o < MO; ++o) {
         double s = 0;
 #pragma unroll
-        for (int l = 0; l < MI; ++l) s += M[o * MI + l] * r[l];
+        for (int l = 0; l < MI; ++l) s += mat_at<MAT>(M, o * MI + l) * r[l];
         if (ACC) out[obase + o * ostr] += s; else out[obase + o * ostr] = s;
       }
     }
@@ -37,7 +66,7 @@ __device__ __forceinline__ void contract_t(double* __restrict__ out, const doubl
       const int base = (DIR == 0 ? 0 : i) + N0 * ((DIR == 1 ? 0 : j) + N1 * (DIR == 2 ? 0 : k));
       double s = 0;
 #pragma unroll
-      for (int l = 0; l < MI; ++l) s += M[r * MI + l] * in[base + l * istr];
+      for (int l = 0; l < MI; ++l) s += M[r * MI + l] * in[base + l * istr];   // (2-D path: per-thread row index -> shared memory)
       if (ACC) out[idx] += s; else out[idx] = s;
     }
   }
@@ -73,20 +102,20 @@ __global__ void k_opdiv_t(CPtr3 u, double* __restrict__ p, const double* __restr
     if (in_mul) { const double* mk = in_mask.p[c] + e * np1; const double* bi = in_mul + e * np1; for (int i = threadIdx.x; i < np1; i += blockDim.x) U[i] = uc[i] * bi[i] * mk[i]; }
     else for (int i = threadIdx.x; i < np1; i += blockDim.x) U[i] = uc[i];
     __syncthreads();
-    contract_t<q, n, 0, false, n, n, nz>(A, U, sDm);
-    contract_t<q, n, 0, false, n, n, nz>(B, U, sI);
+    contract_t<q, n, 0, false, n, n, nz, MAT_D12>(A, U, sDm);
+    contract_t<q, n, 0, false, n, n, nz, MAT_I12>(B, U, sI);
     if constexpr (DIM == 2) {
-      contract_t<q, n, 1, false, q, n, 1>(T0, A, sI);
-      contract_t<q, n, 1, false, q, n, 1>(T1, B, sDm);
+      contract_t<q, n, 1, false, q, n, 1, MAT_I12>(T0, A, sI);
+      contract_t<q, n, 1, false, q, n, 1, MAT_D12>(T1, B, sDm);
       for (int i = threadIdx.x; i < np2; i += blockDim.x) acc[i] += rw[(0 * d + c) * np2 + i] * T0[i] + rw[(1 * d + c) * np2 + i] * T1[i];
       __syncthreads();
     } else {
-      contract_t<q, n, 1, false, q, n, n>(T0, A, sI);
-      contract_t<q, n, 1, false, q, n, n>(T1, B, sDm);
-      contract_t<q, n, 1, false, q, n, n>(T2, B, sI);
-      contract_t<q, n, 2, false, q, q, n>(A, T0, sI);
-      contract_t<q, n, 2, false, q, q, n>(B, T1, sI);
-      contract_t<q, n, 2, false, q, q, n>(U, T2, sDm);
+      contract_t<q, n, 1, false, q, n, n, MAT_I12>(T0, A, sI);
+      contract_t<q, n, 1, false, q, n, n, MAT_D12>(T1, B, sDm);
+      contract_t<q, n, 1, false, q, n, n, MAT_I12>(T2, B, sI);
+      contract_t<q, n, 2, false, q, q, n, MAT_I12>(A, T0, sI);
+      contract_t<q, n, 2, false, q, q, n, MAT_I12>(B, T1, sI);
+      contract_t<q, n, 2, false, q, q, n, MAT_D12>(U, T2, sDm);
       for (int i = threadIdx.x; i < np2; i += blockDim.x)
         acc[i] += rw[(0 * d + c) * np2 + i] * A[i] + rw[(1 * d + c) * np2 + i] * B[i] + rw[(2 * d + c) * np2 + i] * U[i];
       __syncthreads();
@@ -121,21 +150,21 @@ __global__ void k_opgradt_t(const double* __restrict__ p, Ptr3 w, const double* 
     __syncthreads();
     double* wc = w.p[c] + e * np1;
     if constexpr (DIM == 2) {
-      contract_t<n, q, 0, false, q, q, 1>(A0, S0, sDt);
-      contract_t<n, q, 0, false, q, q, 1>(A1, S1, sIt);
-      contract_t<n, q, 1, false, n, q, 1>(S0, A0, sIt);
-      contract_t<n, q, 1, true, n, q, 1>(S0, A1, sDt);
+      contract_t<n, q, 0, false, q, q, 1, MAT_D12T>(A0, S0, sDt);
+      contract_t<n, q, 0, false, q, q, 1, MAT_I12T>(A1, S1, sIt);
+      contract_t<n, q, 1, false, n, q, 1, MAT_I12T>(S0, A0, sIt);
+      contract_t<n, q, 1, true, n, q, 1, MAT_D12T>(S0, A1, sDt);
       for (int i = threadIdx.x; i < np1; i += blockDim.x) wc[i] = S0[i];
       __syncthreads();
     } else {
-      contract_t<n, q, 0, false, q, q, q>(A0, S0, sDt);
-      contract_t<n, q, 0, false, q, q, q>(A1, S1, sIt);
-      contract_t<n, q, 0, false, q, q, q>(A2, S2, sIt);
-      contract_t<n, q, 1, false, n, q, q>(S0, A0, sIt);
-      contract_t<n, q, 1, true, n, q, q>(S0, A1, sDt);
-      contract_t<n, q, 1, false, n, q, q>(S1, A2, sIt);
-      contract_t<n, q, 2, false, n, n, q>(A0, S0, sIt);
-      contract_t<n, q, 2, true, n, n, q>(A0, S1, sDt);
+      contract_t<n, q, 0, false, q, q, q, MAT_D12T>(A0, S0, sDt);
+      contract_t<n, q, 0, false, q, q, q, MAT_I12T>(A1, S1, sIt);
+      contract_t<n, q, 0, false, q, q, q, MAT_I12T>(A2, S2, sIt);
+      contract_t<n, q, 1, false, n, q, q, MAT_I12T>(S0, A0, sIt);
+      contract_t<n, q, 1, true, n, q, q, MAT_D12T>(S0, A1, sDt);
+      contract_t<n, q, 1, false, n, q, q, MAT_I12T>(S1, A2, sIt);
+      contract_t<n, q, 2, false, n, n, q, MAT_I12T>(A0, S0, sIt);
+      contract_t<n, q, 2, true, n, n, q, MAT_D12T>(A0, S1, sDt);
       for (int i = threadIdx.x; i < np1; i += blockDim.x) wc[i] = A0[i];
       __syncthreads();
     }
@@ -160,12 +189,12 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
     for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = cc[i];
     __syncthreads();
     if constexpr (DIM == 2) {
-      contract_t<m, n, 0, false, n, n, 1>(W2, W1, sI);
-      contract_t<m, n, 1, false, m, n, 1>(TR + c * npd, W2, sI);
+      contract_t<m, n, 0, false, n, n, 1, MAT_I1D>(W2, W1, sI);
+      contract_t<m, n, 1, false, m, n, 1, MAT_I1D>(TR + c * npd, W2, sI);
     } else {
-      contract_t<m, n, 0, false, n, n, n>(W2, W1, sI);
-      contract_t<m, n, 1, false, m, n, n>(W1, W2, sI);
-      contract_t<m, n, 2, false, m, m, n>(TR + c * npd, W1, sI);
+      contract_t<m, n, 0, false, n, n, n, MAT_I1D>(W2, W1, sI);
+      contract_t<m, n, 1, false, m, n, n, MAT_I1D>(W1, W2, sI);
+      contract_t<m, n, 2, false, m, m, n, MAT_I1D>(TR + c * npd, W1, sI);
     }
   }
   const double* rx = rxd + e * (size_t)(d * d) * npd;
@@ -186,30 +215,30 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
     for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = uf[i];
     __syncthreads();
     if constexpr (DIM == 2) {
-      contract_t<m, n, 0, false, n, n, 1>(W2, W1, sI);
-      contract_t<m, n, 1, false, m, n, 1>(UF, W2, sI);
-      contract_t<m, m, 0, false, m, m, 1>(W1, UF, sDd);
-      contract_t<m, m, 1, false, m, m, 1>(W2, UF, sDd);
+      contract_t<m, n, 0, false, n, n, 1, MAT_I1D>(W2, W1, sI);
+      contract_t<m, n, 1, false, m, n, 1, MAT_I1D>(UF, W2, sI);
+      contract_t<m, m, 0, false, m, m, 1, MAT_DD>(W1, UF, sDd);
+      contract_t<m, m, 1, false, m, m, 1, MAT_DD>(W2, UF, sDd);
       for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] = TR[i] * W1[i] + TR[npd + i] * W2[i];
       __syncthreads();
-      contract_t<n, m, 0, false, m, m, 1>(W1, ACC, sIt);
-      contract_t<n, m, 1, false, n, m, 1>(W2, W1, sIt);
+      contract_t<n, m, 0, false, m, m, 1, MAT_I1DT>(W1, ACC, sIt);
+      contract_t<n, m, 1, false, n, m, 1, MAT_I1DT>(W2, W1, sIt);
     } else {
-      contract_t<m, n, 0, false, n, n, n>(W2, W1, sI);
-      contract_t<m, n, 1, false, m, n, n>(W1, W2, sI);
-      contract_t<m, n, 2, false, m, m, n>(UF, W1, sI);
-      contract_t<m, m, 0, false, m, m, m>(W1, UF, sDd);
+      contract_t<m, n, 0, false, n, n, n, MAT_I1D>(W2, W1, sI);
+      contract_t<m, n, 1, false, m, n, n, MAT_I1D>(W1, W2, sI);
+      contract_t<m, n, 2, false, m, m, n, MAT_I1D>(UF, W1, sI);
+      contract_t<m, m, 0, false, m, m, m, MAT_DD>(W1, UF, sDd);
       for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] = TR[i] * W1[i];
       __syncthreads();
-      contract_t<m, m, 1, false, m, m, m>(W1, UF, sDd);
+      contract_t<m, m, 1, false, m, m, m, MAT_DD>(W1, UF, sDd);
       for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] += TR[npd + i] * W1[i];
       __syncthreads();
-      contract_t<m, m, 2, false, m, m, m>(W1, UF, sDd);
+      contract_t<m, m, 2, false, m, m, m, MAT_DD>(W1, UF, sDd);
       for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] += TR[2 * npd + i] * W1[i];
       __syncthreads();
-      contract_t<n, m, 0, false, m, m, m>(W1, ACC, sIt);
-      contract_t<n, m, 1, false, n, m, m>(UF, W1, sIt);
-      contract_t<n, m, 2, false, n, n, m>(W2, UF, sIt);
+      contract_t<n, m, 0, false, m, m, m, MAT_I1DT>(W1, ACC, sIt);
+      contract_t<n, m, 1, false, n, m, m, MAT_I1DT>(UF, W1, sIt);
+      contract_t<n, m, 2, false, n, n, m, MAT_I1DT>(W2, UF, sIt);
     }
     double* of = out.p[f] + e * np1;
     for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[i];
@@ -239,14 +268,14 @@ __global__ void k_convect_adj_t(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __res
       double* dst = pass == 0 ? CF : UF;
       for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = src[i];
       __syncthreads();
-      if constexpr (DIM == 2) { contract_t<m, n, 0, false, n, n, 1>(W2, W1, sI); contract_t<m, n, 1, false, m, n, 1>(dst, W2, sI); }
-      else { contract_t<m, n, 0, false, n, n, n>(W2, W1, sI); contract_t<m, n, 1, false, m, n, n>(W1, W2, sI); contract_t<m, n, 2, false, m, m, n>(dst, W1, sI); }
+      if constexpr (DIM == 2) { contract_t<m, n, 0, false, n, n, 1, MAT_I1D>(W2, W1, sI); contract_t<m, n, 1, false, m, n, 1, MAT_I1D>(dst, W2, sI); }
+      else { contract_t<m, n, 0, false, n, n, n, MAT_I1D>(W2, W1, sI); contract_t<m, n, 1, false, m, n, n, MAT_I1D>(W1, W2, sI); contract_t<m, n, 2, false, m, m, n, MAT_I1D>(dst, W1, sI); }
     }
 #pragma unroll
     for (int k = 0; k < d; ++k) {
-      if (k == 0) contract_t<m, m, 0, false, m, m, mz>(W1, UF, sDd);
-      else if (k == 1) contract_t<m, m, 1, false, m, m, mz>(W1, UF, sDd);
-      else contract_t<m, m, 2, false, m, m, mz>(W1, UF, sDd);
+      if (k == 0) contract_t<m, m, 0, false, m, m, mz, MAT_DD>(W1, UF, sDd);
+      else if (k == 1) contract_t<m, m, 1, false, m, m, mz, MAT_DD>(W1, UF, sDd);
+      else contract_t<m, m, 2, false, m, m, mz, MAT_DD>(W1, UF, sDd);
       for (int i = threadIdx.x; i < npd; i += blockDim.x) {
         double g = CF[i] * W1[i];
 #pragma unroll
@@ -257,8 +286,8 @@ __global__ void k_convect_adj_t(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __res
   }
 #pragma unroll 1
   for (int c = 0; c < d; ++c) {
-    if constexpr (DIM == 2) { contract_t<n, m, 0, false, m, m, 1>(W1, AC + c * npd, sIt); contract_t<n, m, 1, false, n, m, 1>(W2, W1, sIt); }
-    else { contract_t<n, m, 0, false, m, m, m>(W1, AC + c * npd, sIt); contract_t<n, m, 1, false, n, m, m>(UF, W1, sIt); contract_t<n, m, 2, false, n, n, m>(W2, UF, sIt); }
+    if constexpr (DIM == 2) { contract_t<n, m, 0, false, m, m, 1, MAT_I1DT>(W1, AC + c * npd, sIt); contract_t<n, m, 1, false, n, m, 1, MAT_I1DT>(W2, W1, sIt); }
+    else { contract_t<n, m, 0, false, m, m, m, MAT_I1DT>(W1, AC + c * npd, sIt); contract_t<n, m, 1, false, n, m, m, MAT_I1DT>(UF, W1, sIt); contract_t<n, m, 2, false, n, n, m, MAT_I1DT>(W2, UF, sIt); }
     double* of = out.p[c] + e * np1;
     for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[i];
     __syncthreads();
@@ -324,6 +353,7 @@ bool tp_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, const double*
   size_t smem = (size_t)(2 * dm.q * dm.n + 7 * dm.np1) * sizeof(double);
   if (smem > 220 * 1024) return false;
   CPtr3 mk{{dm.mask[0], dm.mask[1], dm.mask[2]}};
+  ensure_const_ops(dm, st);
   int thr = tp_threads(dm.n, dm.ndim, dm.np1);
 #define FN(N_, D_) { static bool s_ = false; if (!s_) { set_smem(k_opdiv_t<N_, D_>, smem); s_ = true; } k_opdiv_t<N_, D_><<<(unsigned)dm.E, thr, smem, st>>>(u, p, dm.rxw2, dm.I12, dm.D12, scale, in_mul, mk, out_mul); }
   TP_SWITCH_N(dm.n * 10 + dm.ndim)
@@ -333,6 +363,7 @@ bool tp_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, const double*
 bool tp_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st) {
   size_t smem = (size_t)(2 * dm.q * dm.n + 7 * dm.np1) * sizeof(double);
   if (smem > 220 * 1024) return false;
+  ensure_const_ops(dm, st);
   int thr = tp_threads(dm.n, dm.ndim, dm.np1);
 #define FN(N_, D_) { static bool s_ = false; if (!s_) { set_smem(k_opgradt_t<N_, D_>, smem); s_ = true; } k_opgradt_t<N_, D_><<<(unsigned)dm.E, thr, smem, st>>>(p, w, dm.rxw2, dm.I12t, dm.D12t); }
   TP_SWITCH_N(dm.n * 10 + dm.ndim)
@@ -356,6 +387,7 @@ bool tp_schwarz_fdm(const DevMesh& dm, const double* w, double* z, double* t, cu
 bool tp_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double alpha, int accumulate, cudaStream_t st) {
   size_t smem = (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * dm.npd) * sizeof(double);
   if (smem > 220 * 1024) return false;
+  ensure_const_ops(dm, st);
   int thr = tp_threads(dm.m, dm.ndim, dm.npd);
 #define FN(N_, M_, D_) { static bool s_ = false; if (!s_) { set_smem(k_convect_t<N_, M_, D_>, smem); s_ = true; } k_convect_t<N_, M_, D_><<<(unsigned)dm.E, thr, smem, st>>>(u, nf, C, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, alpha, accumulate); }
   TP_SWITCH_NM((dm.n * 100 + dm.m) * 10 + dm.ndim)
@@ -365,6 +397,7 @@ bool tp_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double al
 bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st) {
   size_t smem = (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * dm.npd) * sizeof(double);
   if (smem > 220 * 1024) return false;
+  ensure_const_ops(dm, st);
   int thr = tp_threads(dm.m, dm.ndim, dm.npd);
 #define FN(N_, M_, D_) { static bool s_ = false; if (!s_) { set_smem(k_convect_adj_t<N_, M_, D_>, smem); s_ = true; } k_convect_adj_t<N_, M_, D_><<<(unsigned)dm.E, thr, smem, st>>>(U, c, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, alpha, accumulate); }
   TP_SWITCH_NM((dm.n * 100 + dm.m) * 10 + dm.ndim)
