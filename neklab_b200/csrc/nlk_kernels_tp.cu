@@ -171,6 +171,210 @@ __global__ void k_opgradt_t(const double* __restrict__ p, Ptr3 w, const double* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K5, 3-D stage-fused versions
+// The independent contractions of one sum-factorisation stage run concurrently on different warp groups (3 x P threads),
+// the last stage is fused with the metric contraction / the global store: 3 barriers per component instead of 8-9 and
+// 5-6 element tiles in shared memory instead of 7 (higher occupancy).  Pencil = all points along the contracted direction.
+__host__ __device__ constexpr int roundup32(int x) { return (x + 31) / 32 * 32; }
+
+// one pencil: r[] (already loaded) -> MO outputs written with stride ostr; optional second operand pair accumulates
+template <int MO, int MI, int MAT>
+__device__ __forceinline__ void pen_apply(const double (&r)[MI], double (&o)[MO]) {
+#pragma unroll
+  for (int a = 0; a < MO; ++a) {
+    double s = 0;
+#pragma unroll
+    for (int l = 0; l < MI; ++l) s += mat_at<MAT>(nullptr, a * MI + l) * r[l];
+    o[a] += s;
+  }
+}
+
+// Software L2 prefetch of a future element's operands: blocks are short-lived, so instead of an in-block pipeline every
+// block pulls the lines that the block `dist` elements ahead will need into the 126 MB L2 (DRAM latency -> L2 latency).
+__device__ __forceinline__ void prefetch_l2(const double* base, int ndoubles, int t, int nthreads) {
+  const char* p = reinterpret_cast<const char*>(base);
+  for (int off = t * 128; off < ndoubles * 8; off += nthreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+}
+constexpr int PF_DIST = 296;      // elements ahead (~2 waves of resident blocks)
+__device__ __forceinline__ void group_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// Component-parallel layout: warp group g (P threads, named barrier g+1) carries velocity component g through all three
+// sum-factorisation stages on its own shared-memory tiles; the three partial divergences are summed at the end.
+template <int N>
+__global__ void __launch_bounds__(3 * roundup32(N * N))
+k_opdiv3_t(CPtr3 u, double* __restrict__ p, const double* __restrict__ rxw2, double scale, const double* __restrict__ in_mul, CPtr3 in_mask,
+           const double* __restrict__ out_mul) {
+  constexpr int n = N, q = N - 2, np1 = n * n * n, np2 = q * q * q, P = roundup32(n * n);
+  constexpr int qp = q | 1, npad = n | 1;            // odd pitches: conflict-free pencil accesses
+  constexpr int TILE = npad * n * n + 2 * qp * n * n + 2 * q * q * n;
+  extern __shared__ double sm[];
+  const size_t e = blockIdx.x;
+  const int tid = threadIdx.x, c = tid / P, t = tid - c * P;
+  double* U = sm + c * TILE; double* A = U + npad * n * n; double* B = A + qp * n * n; double* T1 = B + qp * n * n; double* T2 = T1 + q * q * n;
+  double* T0 = U;
+  double* R = sm + 3 * TILE;                         // [3][np2] partial results
+  const double* rw = rxw2 + e * (size_t)9 * np2;
+  if (e + PF_DIST < gridDim.x) {
+    const size_t en = e + PF_DIST;
+    prefetch_l2(u.p[c] + en * np1, np1, t, P);
+    if (in_mul) { prefetch_l2(in_mask.p[c] + en * np1, np1, t, P); if (c == 0) prefetch_l2(in_mul + en * np1, np1, t, P); }
+    prefetch_l2(rxw2 + en * (size_t)9 * np2 + (size_t)c * 3 * np2, 3 * np2, t, P);
+  }
+  // metrics for the z stage, fetched first (consumed last)
+  double m0[q], m1[q], m2[q];
+  if (t < q * q) {
+#pragma unroll
+    for (int a = 0; a < q; ++a) { const int g = a * q * q + t; m0[a] = rw[(0 * 3 + c) * np2 + g]; m1[a] = rw[(1 * 3 + c) * np2 + g]; m2[a] = rw[(2 * 3 + c) * np2 + g]; }
+  }
+  {
+    const double* uc = u.p[c] + e * np1;
+    if (in_mul) { const double* mk = in_mask.p[c] + e * np1; const double* bi = in_mul + e * np1; for (int i = t; i < np1; i += P) U[(i / n) * npad + (i % n)] = uc[i] * bi[i] * mk[i]; }
+    else for (int i = t; i < np1; i += P) U[(i / n) * npad + (i % n)] = uc[i];
+  }
+  group_sync(c + 1, P);
+  // ---- x stage: A = D12_x u, B = I12_x u
+  if (t < n * n) {
+    double r[n], o[q];
+#pragma unroll
+    for (int l = 0; l < n; ++l) r[l] = U[t * npad + l];
+#pragma unroll
+    for (int a = 0; a < q; ++a) o[a] = 0.0;
+    pen_apply<q, n, MAT_D12>(r, o);
+#pragma unroll
+    for (int a = 0; a < q; ++a) { A[t * qp + a] = o[a]; o[a] = 0.0; }
+    pen_apply<q, n, MAT_I12>(r, o);
+#pragma unroll
+    for (int a = 0; a < q; ++a) B[t * qp + a] = o[a];
+  }
+  group_sync(c + 1, P);
+  // ---- y stage: T0 = I12_y A, T1 = D12_y B, T2 = I12_y B
+  if (t < q * n) {
+    const int iq = t % q, k = t / q;
+    double r[n], o[q];
+#pragma unroll
+    for (int l = 0; l < n; ++l) r[l] = A[(l + n * k) * qp + iq];
+#pragma unroll
+    for (int a = 0; a < q; ++a) o[a] = 0.0;
+    pen_apply<q, n, MAT_I12>(r, o);
+#pragma unroll
+    for (int a = 0; a < q; ++a) { T0[iq + q * (a + q * k)] = o[a]; o[a] = 0.0; }
+#pragma unroll
+    for (int l = 0; l < n; ++l) r[l] = B[(l + n * k) * qp + iq];
+    pen_apply<q, n, MAT_D12>(r, o);
+#pragma unroll
+    for (int a = 0; a < q; ++a) { T1[iq + q * (a + q * k)] = o[a]; o[a] = 0.0; }
+    pen_apply<q, n, MAT_I12>(r, o);
+#pragma unroll
+    for (int a = 0; a < q; ++a) T2[iq + q * (a + q * k)] = o[a];
+  }
+  group_sync(c + 1, P);
+  // ---- z stage fused with the metric contraction
+  if (t < q * q) {
+    double r[n], d0[q], acc[q];
+#pragma unroll
+    for (int l = 0; l < n; ++l) r[l] = T0[t + q * q * l];
+#pragma unroll
+    for (int a = 0; a < q; ++a) d0[a] = 0.0;
+    pen_apply<q, n, MAT_I12>(r, d0);
+#pragma unroll
+    for (int a = 0; a < q; ++a) { acc[a] = m0[a] * d0[a]; d0[a] = 0.0; }
+#pragma unroll
+    for (int l = 0; l < n; ++l) r[l] = T1[t + q * q * l];
+    pen_apply<q, n, MAT_I12>(r, d0);
+#pragma unroll
+    for (int a = 0; a < q; ++a) { acc[a] += m1[a] * d0[a]; d0[a] = 0.0; }
+#pragma unroll
+    for (int l = 0; l < n; ++l) r[l] = T2[t + q * q * l];
+    pen_apply<q, n, MAT_D12>(r, d0);
+#pragma unroll
+    for (int a = 0; a < q; ++a) R[c * np2 + a * q * q + t] = acc[a] + m2[a] * d0[a];
+  }
+  __syncthreads();
+  for (int i = tid; i < np2; i += blockDim.x) {
+    const double v = scale * (R[i] + R[np2 + i] + R[2 * np2 + i]);
+    p[e * np2 + i] = out_mul ? v * out_mul[e * np2 + i] : v;
+  }
+}
+
+// Component-parallel: warp group g produces w_g = D_g^T p.
+template <int N>
+__global__ void __launch_bounds__(3 * roundup32(N * N))
+k_opgradt3_t(const double* __restrict__ p, Ptr3 w, const double* __restrict__ rxw2) {
+  constexpr int n = N, q = N - 2, np1 = n * n * n, np2 = q * q * q, P = roundup32(n * n);
+  constexpr int npad = n | 1, qp = q | 1;
+  constexpr int TILE = 3 * qp * q * q + 3 * npad * q * q + 2 * n * n * q;
+  extern __shared__ double sm[];
+  const size_t e = blockIdx.x;
+  const int tid = threadIdx.x, c = tid / P, t = tid - c * P;
+  double* S = sm + c * TILE; double* A0 = S + 3 * qp * q * q; double* A1 = A0 + npad * q * q; double* A2 = A1 + npad * q * q;
+  double* B0 = A2 + npad * q * q; double* B1 = B0 + n * n * q;
+  const double* rw = rxw2 + e * (size_t)9 * np2;
+  const double* pe = p + e * np2;
+  if (e + PF_DIST < gridDim.x) {
+    const size_t en = e + PF_DIST;
+    if (c == 0) prefetch_l2(p + en * np2, np2, t, P);
+    prefetch_l2(rxw2 + en * (size_t)9 * np2 + (size_t)c * 3 * np2, 3 * np2, t, P);
+  }
+  // S_k = p * rxw2[k][c], k = 0..2, coalesced into padded tiles
+  for (int i = t; i < 3 * np2; i += P) {
+    const int k = i / np2, r_ = i - k * np2;
+    S[k * qp * q * q + (r_ / q) * qp + (r_ % q)] = pe[r_] * rw[(size_t)(k * 3 + c) * np2 + r_];
+  }
+  group_sync(c + 1, P);
+  // ---- x stage: A0 = D12^T_x S0, A1 = I12^T_x S1, A2 = I12^T_x S2       pencils (jq,kq)
+  if (t < q * q) {
+    double r[q], o[n];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int l = 0; l < q; ++l) r[l] = S[k * qp * q * q + t * qp + l];
+#pragma unroll
+      for (int a = 0; a < n; ++a) o[a] = 0.0;
+      if (k == 0) pen_apply<n, q, MAT_D12T>(r, o); else pen_apply<n, q, MAT_I12T>(r, o);
+      double* dst = (k == 0 ? A0 : (k == 1 ? A1 : A2)) + t * npad;
+#pragma unroll
+      for (int a = 0; a < n; ++a) dst[a] = o[a];
+    }
+  }
+  group_sync(c + 1, P);
+  // ---- y stage: B0 = I12^T_y A0 + D12^T_y A1 ; B1 = I12^T_y A2            pencils (i,kq)
+  if (t < n * q) {
+    const int i = t % n, k = t / n;
+    double r[q], o[n];
+#pragma unroll
+    for (int a = 0; a < n; ++a) o[a] = 0.0;
+#pragma unroll
+    for (int l = 0; l < q; ++l) r[l] = A0[(l + q * k) * npad + i];
+    pen_apply<n, q, MAT_I12T>(r, o);
+#pragma unroll
+    for (int l = 0; l < q; ++l) r[l] = A1[(l + q * k) * npad + i];
+    pen_apply<n, q, MAT_D12T>(r, o);
+#pragma unroll
+    for (int a = 0; a < n; ++a) { B0[i + n * (a + n * k)] = o[a]; o[a] = 0.0; }
+#pragma unroll
+    for (int l = 0; l < q; ++l) r[l] = A2[(l + q * k) * npad + i];
+    pen_apply<n, q, MAT_I12T>(r, o);
+#pragma unroll
+    for (int a = 0; a < n; ++a) B1[i + n * (a + n * k)] = o[a];
+  }
+  group_sync(c + 1, P);
+  // ---- z stage: w = I12^T_z B0 + D12^T_z B1, stored straight to HBM        pencils (i,j)
+  if (t < n * n) {
+    double r[q], o[n];
+#pragma unroll
+    for (int a = 0; a < n; ++a) o[a] = 0.0;
+#pragma unroll
+    for (int l = 0; l < q; ++l) r[l] = B0[t + n * n * l];
+    pen_apply<n, q, MAT_I12T>(r, o);
+#pragma unroll
+    for (int l = 0; l < q; ++l) r[l] = B1[t + n * n * l];
+    pen_apply<n, q, MAT_D12T>(r, o);
+    double* wc = w.p[c] + e * np1;
+#pragma unroll
+    for (int a = 0; a < n; ++a) wc[t + n * n * a] = o[a];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K3 convect
 template <int N, int MD, int DIM>
 __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __restrict__ rxd, const double* __restrict__ I1dg,
@@ -354,6 +558,14 @@ bool tp_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, const double*
   if (smem > 220 * 1024) return false;
   CPtr3 mk{{dm.mask[0], dm.mask[1], dm.mask[2]}};
   ensure_const_ops(dm, st);
+  if (dm.ndim == 3) {
+    const int n = dm.n, q = dm.q;
+    size_t sm3 = (size_t)(3 * ((n | 1) * n * n + 2 * (q | 1) * n * n + 2 * q * q * n) + 3 * q * q * q) * sizeof(double);
+    int thr3 = 3 * roundup32(n * n);
+#define FN3(N_) case N_: { static bool s_ = false; if (!s_) { set_smem(k_opdiv3_t<N_>, sm3); s_ = true; } k_opdiv3_t<N_><<<(unsigned)dm.E, thr3, sm3, st>>>(u, p, dm.rxw2, scale, in_mul, mk, out_mul); ++g_launches; return true; }
+    switch (n) { FN3(4) FN3(5) FN3(6) FN3(7) FN3(8) FN3(9) FN3(10) default: break; }
+#undef FN3
+  }
   int thr = tp_threads(dm.n, dm.ndim, dm.np1);
 #define FN(N_, D_) { static bool s_ = false; if (!s_) { set_smem(k_opdiv_t<N_, D_>, smem); s_ = true; } k_opdiv_t<N_, D_><<<(unsigned)dm.E, thr, smem, st>>>(u, p, dm.rxw2, dm.I12, dm.D12, scale, in_mul, mk, out_mul); }
   TP_SWITCH_N(dm.n * 10 + dm.ndim)
@@ -364,6 +576,14 @@ bool tp_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st) {
   size_t smem = (size_t)(2 * dm.q * dm.n + 7 * dm.np1) * sizeof(double);
   if (smem > 220 * 1024) return false;
   ensure_const_ops(dm, st);
+  if (dm.ndim == 3) {
+    const int n = dm.n, q = dm.q;
+    size_t sm3 = (size_t)(3 * (3 * (q | 1) * q * q + 3 * (n | 1) * q * q + 2 * n * n * q)) * sizeof(double);
+    int thr3 = 3 * roundup32(n * n);
+#define FN3(N_) case N_: { static bool s_ = false; if (!s_) { set_smem(k_opgradt3_t<N_>, sm3); s_ = true; } k_opgradt3_t<N_><<<(unsigned)dm.E, thr3, sm3, st>>>(p, w, dm.rxw2); ++g_launches; return true; }
+    switch (n) { FN3(4) FN3(5) FN3(6) FN3(7) FN3(8) FN3(9) FN3(10) default: break; }
+#undef FN3
+  }
   int thr = tp_threads(dm.n, dm.ndim, dm.np1);
 #define FN(N_, D_) { static bool s_ = false; if (!s_) { set_smem(k_opgradt_t<N_, D_>, smem); s_ = true; } k_opgradt_t<N_, D_><<<(unsigned)dm.E, thr, smem, st>>>(p, w, dm.rxw2, dm.I12t, dm.D12t); }
   TP_SWITCH_N(dm.n * 10 + dm.ndim)
