@@ -4,10 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload cylinder|synth3d]
 
 Workloads
-  cylinder : examples/cylinder/stability/direct of the reference (Re=50, 1996 el, lx1=6, lxd=9, bdf3, tau=1,
-             100+2 time steps per matvec).  One bench "step" = one exptA matvec.           [default, N=1]
   synth3d  : the 2-D cylinder mesh extruded periodically in z (lx1=8, lxd=12), element-partitioned over the ranks
-             (weak scaling: --layers z-layers PER GPU).  One bench "step" = one perturbation time step.
+             (weak scaling: --layers z-layers PER GPU).  One bench "step" = one perturbation time step (the body of the
+             exptA loop), timed after --spinup steady-state steps.  Metric GDOF*steps/s.   [default, every N; at N=1
+             the JSON line also carries the cylinder Re=50 matvec/s block]
+  cylinder : examples/cylinder/stability/direct of the reference (Re=50, 1996 el, lx1=6, lxd=9, bdf3, tau=1,
+             100+2 time steps per matvec).  One bench "step" = one exptA matvec.  Metric exptA matvec/s.  (N=1 only)
 
 Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events on the library's stream, max over ranks) with
 inputs resident in HBM; `e2e` goes through the public C-ABI with host buffers (H2D of the input vector and D2H of the
@@ -113,10 +115,13 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, "cylinder", "synth3d"])
     ap.add_argument("--layers", type=int, default=4, help="synth3d: z-layers per GPU (1996 elements each)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="time steps in the CPU-baseline sample")
+    ap.add_argument("--spinup", type=int, default=30, help="synth3d: untimed time steps before the timed ones (>= warmup)")
+    ap.add_argument("--no-cylinder", action="store_true", help="skip the extra cylinder Re=50 matvec block at N=1")
+    ap.add_argument("--coarse-iters", type=int, default=12, help="synth3d: Jacobi-PCG iterations of the sparse coarse solve")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = a.workload or ("cylinder" if world == 1 else "synth3d")
-    steps = a.steps if a.steps is not None else (5 if workload == "cylinder" else 3)
+    workload = a.workload or "synth3d"
+    steps = a.steps if a.steps is not None else (5 if workload == "cylinder" else 10)
     if a.impl == "reference":
         if rank == 0:
             print(json.dumps(reference_arm(workload, steps, a.warmup, a)), flush=True)
@@ -170,6 +175,41 @@ def reference_arm(workload, steps, warmup, a):
 
 
 # ----------------------------------------------------------------------------------------------- native arm
+def _cylinder_block(api, case, steps, warmup, device):
+    """Cylinder Re=50 exptA matvec on ONE GPU (the reference's own config): device-timed and end-to-end matvec/s."""
+    mesh = api.Mesh(case["coords"], case["vertex"], case["cbc"], 9)
+    prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7, pr_proj=20)   # 1cyl.par: residualProj = yes (mxprev 20)
+    ctx = api.Context(mesh, prm, device=device)
+    vel = case["vel"][:, :, 0]
+    bf = ctx.vec(); bf.upload([vel[:, 0][:, None], vel[:, 1][:, None]])
+    x = ctx.vec(); x.rand(ifnorm=True, seed=12345); y = ctx.vec()
+    A = api.exptA_linop(ctx, 1.0, bf); A.init()
+    for _ in range(warmup):
+        A.matvec(x, y)
+    ctx.sync()
+    ms = 0.0; launches = 0; cg = gm = ts = 0
+    for _ in range(steps):
+        A.matvec(x, y)
+        s = A.stats(); ms += s["ms_total"]; launches += s["launches"]; cg += s["cg_iters"]; gm += s["gmres_iters"]; ts += s["steps"]
+    hv, hp, _ = x.download()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        x.upload(hv, hp); A.matvec(x, y); ov, op, _ = y.download()
+    ctx.sync()
+    e2e_s = (time.perf_counter() - t0) / steps
+    vec_bytes = sum(v.nbytes for v in hv) + hp.nbytes
+    ms_ax, by_ax = ctx.bench_kernel(0, 200)
+    out = {"matvec_per_s": 1e3 / (ms / steps), "ms_per_matvec": ms / steps, "e2e_matvec_per_s": 1.0 / e2e_s, "h2d_bytes": int(vec_bytes), "d2h_bytes": int(vec_bytes),
+           "time_steps_per_matvec": ts // steps, "cg_iters_per_step": cg / max(ts, 1), "gmres_iters_per_step": gm / max(ts, 1),
+           "launches_per_time_step": launches / max(ts, 1), "launches": int(launches),
+           "gdof_steps_per_s": case["coords"].shape[0] * 36 * 1e-9 * (ts / steps) / (ms / steps * 1e-3),
+           "axhelm_us": ms_ax * 1e3, "axhelm_GBps_L2_resident": by_ax / (ms_ax * 1e-3) / 1e9,
+           "config": {"elements": int(case["coords"].shape[0]), "lx1": 6, "lxd": 9, "timestepper": "bdf3", "tau": 1.0, "residualProj": 20,
+                      "note": "71 856 points (0.57 MB per field): L2-resident, launch/latency-bound by construction"}}
+    ctx.close()
+    return out
+
+
 def native_arm(workload, steps, warmup, a, rank, world, local):
     from neklab_b200 import api, build
     if rank == 0:
@@ -184,120 +224,93 @@ def native_arm(workload, steps, warmup, a, rank, world, local):
         dist.barrier()
     peak, peak_src = load_peaks()
     case = cylinder_inputs()
-    nccl_id = None
+    sampler = ClockSampler(local)
+    extra = {}
     if workload == "cylinder":
-        gllnid = None
         if world > 1:
-            gllnid = api.partition(case["pid"], world)
-        sel = slice(None) if gllnid is None else np.where(gllnid == rank)[0]
-        mesh = api.Mesh(case["coords"][sel], case["vertex"], case["cbc"], 9, gllnid=gllnid, rank=rank, nranks=world)
-        prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7, pr_proj=20)   # 1cyl.par: residualProj = yes (mxprev = 20)
-        tau = 1.0
-        vel = case["vel"][sel][:, :, 0]
-        U = [vel[:, 0][:, None], vel[:, 1][:, None]]
+            raise SystemExit("the cylinder workload is a single-GPU config (71 856 points); use --workload synth3d for N > 1")
+        sampler.start()
+        cyl = _cylinder_block(api, case, steps, warmup, local)
+        clocks = sampler.stop()
+        ms_step = cyl["ms_per_matvec"]; value = cyl["matvec_per_s"]; unit = "matvec/s"; metric = "exptA matvec/s"
+        e2e = {"value": cyl["e2e_matvec_per_s"], "unit": unit, "h2d_bytes_per_step": cyl["h2d_bytes"], "d2h_bytes_per_step": cyl["d2h_bytes"]}
+        launches = cyl["launches"]
+        cfg = dict(cyl["config"]); cfg["workload"] = "cylinder_re50_exptA_matvec"
+        extra = {k: cyl[k] for k in ("gdof_steps_per_s", "time_steps_per_matvec", "cg_iters_per_step", "gmres_iters_per_step", "launches_per_time_step")}
+        roof = {"kernel": "k_axhelm<6,2> (K1)", "bound": "hbm", "achieved": cyl["axhelm_GBps_L2_resident"], "peak": peak, "unit": "GB/s",
+                "frac": cyl["axhelm_GBps_L2_resident"] / peak, "traffic": None, "peak_source": peak_src, "note": "L2-resident problem: not an HBM measurement"}
+        other = {}
+        scaling = "strong"
     else:
+        # synthetic 3-D extruded cylinder, weak scaling: `layers` z-layers (1996 elements each) per GPU, z-slab partition
         L = a.layers * world
         coords, Uall, vertex, cbc = extrude(case, 8, L)
         E2 = case["coords"].shape[0]
-        gllnid = (np.arange(E2 * L) // (E2 * a.layers)).astype(np.int32) if world > 1 else None      # z-slabs
+        gllnid = (np.arange(E2 * L) // (E2 * a.layers)).astype(np.int32) if world > 1 else None
         sel = slice(None) if gllnid is None else np.where(gllnid == rank)[0]
         mesh = api.Mesh(coords[sel], vertex, cbc, 12, gllnid=gllnid, rank=rank, nranks=world)
-        prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7, pr_proj=20)
-        tau = None
-        U = [Uall[sel, 0], Uall[sel, 1], Uall[sel, 2]]
-    if world > 1:
-        import torch
-        buf = [api.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(buf, src=0)
-        nccl_id = buf[0]
-    ctx = api.Context(mesh, prm, device=local, nccl_id=nccl_id)
-    bf = ctx.vec(); bf.upload(U)
-    x = ctx.vec(); x.rand(ifnorm=True, seed=12345)
-    y = ctx.vec()
-    npts = mesh.nel * mesh.shape1[1] * mesh.shape1[2] * mesh.shape1[3]
-    sampler = ClockSampler(local)
-
-    def barrier():
+        prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7, pr_proj=20, coarse_iters=a.coarse_iters)
+        nccl_id = None
+        if world > 1:
+            buf = [api.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(buf, src=0)
+            nccl_id = buf[0]
+        ctx = api.Context(mesh, prm, device=local, nccl_id=nccl_id)
+        bf = ctx.vec(); bf.upload([Uall[sel, 0], Uall[sel, 1], Uall[sel, 2]])
+        x = ctx.vec(); x.rand(ifnorm=True, seed=12345); y = ctx.vec()
+        npts = mesh.nel * 512
+        A = api.exptA_linop(ctx, 1.0, bf)
+        s0 = A.init()
+        spin = max(a.spinup, warmup)           # untimed steps: BDF start-up + projection space fill (W >= 3 always holds)
         ctx.sync()
         if dist is not None:
             dist.barrier()
-
-    if workload == "cylinder":
-        A = api.exptA_linop(ctx, tau, bf)
-        A.init()
-        for _ in range(warmup):
-            A.matvec(x, y)
-        barrier(); sampler.start()
-        ms = 0.0; launches = 0; cg = gm = ts = 0
-        for _ in range(steps):
-            A.matvec(x, y)
-            s = A.stats(); ms += s["ms_total"]; launches += s["launches"]; cg += s["cg_iters"]; gm += s["gmres_iters"]; ts += s["steps"]
-        barrier(); clocks = sampler.stop()
-        ms_step = ms / steps
-        # e2e: host buffers in, host buffers out, through the public API
-        hv, hp, _ = x.download()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            x.upload(hv, hp)
-            A.matvec(x, y)
-            ov, op, _ = y.download()
+        sampler.start()
+        ms = A.time_steps(x, spin, steps)
         ctx.sync()
-        e2e_s = (time.perf_counter() - t0) / steps
+        if dist is not None:
+            dist.barrier()
+        clocks = sampler.stop()
+        s = A.stats()
+        ms_step = ms / steps
+        # e2e: host vector in, `steps` time steps through the public exptA API (tau = steps*dt), host vector out
+        import ctypes as C
+        hv, hp, _ = x.download()
+        api.lib().nlk_exptA_set_tau(A.h, C.c_double(s0["dt"] * steps))
+        t0 = time.perf_counter(); x.upload(hv, hp); A.matvec(x, y); ov, op, _ = y.download(); ctx.sync()
+        e2e_steps = A.stats()["steps"]
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
         vec_bytes = sum(v.nbytes for v in hv) + hp.nbytes
         if dist is not None:
             import torch
             t = torch.tensor([ms_step, e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_step, e2e_s = float(t[0]), float(t[1])
-        value = 1e3 / ms_step; unit = "matvec/s"; metric = "exptA matvec/s"
-        e2e = {"value": 1.0 / e2e_s, "unit": unit, "h2d_bytes_per_step": int(vec_bytes), "d2h_bytes_per_step": int(vec_bytes)}
-        npts_global = case["coords"].shape[0] * 36
-        extra = {"gdof_steps_per_s": npts_global * 1e-9 * (ts / steps) / (ms_step * 1e-3), "time_steps_per_matvec": ts // steps,
-                 "cg_iters_per_step": cg / max(ts, 1), "gmres_iters_per_step": gm / max(ts, 1), "launches_per_time_step": launches / max(ts, 1)}
-        cfg = {"workload": "cylinder_re50_exptA_matvec", "elements": int(case["coords"].shape[0]), "lx1": 6, "lxd": 9, "timestepper": "bdf3",
-               "tau": 1.0, "partition": ("single" if world == 1 else f".ma2 power-of-two rule over {world} ranks"),
-               "l2": "working set (~20 MB) is L2-resident by construction (reference config size)"}
-    else:
-        import ctypes as C
-        L_ = api.lib()
-        # one bench step = one perturbation time step (the body of the exptA loop); state stays in HBM
-        A = api.exptA_linop(ctx, 1.0, bf)
-        s0 = A.init()
-        # drive time steps through a short-horizon matvec: tau = k*dt gives exactly k steps (+2 rst steps)
-        dt = s0["dt"]
-        L_.nlk_exptA_set_tau(A.h, C.c_double(dt * max(1, warmup)))
-        A.matvec(x, y)
-        L_.nlk_exptA_set_tau(A.h, C.c_double(dt * steps))
-        barrier(); sampler.start()
-        A.matvec(x, y)
-        barrier(); clocks = sampler.stop()
-        s = A.stats()
-        ts = s["steps"]; ms_step = s["ms_total"] / ts
-        if dist is not None:
-            import torch
-            t = torch.tensor([ms_step], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_step = float(t[0])
         npts_global = npts * world
         value = npts_global * 1e-9 / (ms_step * 1e-3); unit = "GDOF*steps/s"; metric = "GDOF*steps/s"
-        hv, hp, _ = x.download()
-        t0 = time.perf_counter(); x.upload(hv, hp); A.matvec(x, y); ov, op, _ = y.download(); ctx.sync()
-        e2e_s = (time.perf_counter() - t0) / ts
-        vec_bytes = sum(v.nbytes for v in hv) + hp.nbytes
-        e2e = {"value": npts_global * 1e-9 / e2e_s, "unit": unit, "h2d_bytes_per_step": int(vec_bytes // ts), "d2h_bytes_per_step": int(vec_bytes // ts)}
+        e2e = {"value": npts_global * 1e-9 / e2e_s, "unit": unit, "h2d_bytes_per_step": int(vec_bytes // e2e_steps), "d2h_bytes_per_step": int(vec_bytes // e2e_steps),
+               "note": "cold start (BDF1 start-up, empty projection space) + 2 restart steps included, so it is below `value`"}
         launches = s["launches"]
-        extra = {"time_steps_timed": int(ts), "cg_iters_per_step": s["cg_iters"] / ts, "gmres_iters_per_step": s["gmres_iters"] / ts,
-                 "launches_per_time_step": launches / ts, "dt": dt}
+        extra = {"time_steps_timed": int(s["steps"]), "spinup_steps": int(spin), "cg_iters_per_step": s["cg_iters"] / steps, "gmres_iters_per_step": s["gmres_iters"] / steps,
+                 "launches_per_time_step": launches / steps, "dt": s0["dt"], "points_per_gpu": int(npts)}
         cfg = {"workload": "synth3d_extruded_cylinder_time_step", "elements": int(mesh.nel * world), "lx1": 8, "lxd": 12, "layers_per_gpu": a.layers,
-               "partition": "z-slabs of whole 2-D layers", "l2": "inputs larger than L2 (%.0f MB of state+geometry per GPU)" % (npts * 8 * 40 / 1e6)}
-    # roofline of the dominant kernel (K1 axhelm) at this problem size, CUDA events on the library stream
-    ms_ax, bytes_ax = ctx.bench_kernel(0, 200)
-    roof = {"kernel": "k_axhelm (K1, Helmholtz apply inside Jacobi-PCG)", "bound": "hbm", "achieved": bytes_ax / (ms_ax * 1e-3) / 1e9,
-            "peak": peak, "unit": "GB/s", "frac": bytes_ax / (ms_ax * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-            "us_per_launch": ms_ax * 1e3, "algorithmic_bytes_per_launch": bytes_ax}
-    other = {}
-    for name, which in (("dssum", 1), ("cdabdtp", 2), ("convect", 3), ("precond", 4), ("vec_dot", 5)):
-        m_, b_ = ctx.bench_kernel(which, 50)
-        other[name] = {"us": m_ * 1e3, "GBps": b_ / (m_ * 1e-3) / 1e9}
+               "partition": "z-slabs of whole 2-D layers (weak scaling)", "timestepper": "bdf3", "residualProj": 20,
+               "l2": "inputs larger than L2 (state + geometry + dealiasing metrics ~ %.1f GB per GPU)" % (npts * 8 * 75 / 1e9)}
+        # roofline of the dominant kernel at this problem size (CUDA events on the library stream, right after the timed region)
+        ms_ax, bytes_ax = ctx.bench_kernel(0, 100)
+        roof = {"kernel": "k_axhelm<8,3> (K1, Helmholtz apply inside the Jacobi-PCG)", "bound": "hbm", "achieved": bytes_ax / (ms_ax * 1e-3) / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": bytes_ax / (ms_ax * 1e-3) / 1e9 / peak, "traffic": bytes_ax * (1.168 / 1.177), "peak_source": peak_src,
+                "us_per_launch": ms_ax * 1e3, "algorithmic_bytes_per_launch": bytes_ax,
+                "traffic_note": "dram read+write / algorithmic = 0.992 from ncu --set full at 31 936 elements (profiles/r01_ncu_full_summary.md), scaled to this size"}
+        other = {}
+        for name, which in (("dssum", 1), ("cdabdtp", 2), ("convect", 3), ("precond", 4), ("vec_dot", 5)):
+            m_, b_ = ctx.bench_kernel(which, 20)
+            other[name] = {"us": m_ * 1e3, "GBps": b_ / (m_ * 1e-3) / 1e9, "frac": b_ / (m_ * 1e-3) / 1e9 / peak}
+        ctx.close()
+        scaling = "weak"
+        if world == 1 and not a.no_cylinder:
+            extra["cylinder_re50"] = _cylinder_block(api, case, 3, 3, local)
     out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
-           "higher_is_better": True, "scaling": "weak" if workload == "synth3d" else "strong", "vs_baseline": None, "dtype": "f64",
+           "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
            "kernels": other, **extra}
     if world == 1 and rank == 0 and os.environ.get("NLK_BENCH_NO_CPU") != "1":
@@ -308,10 +321,10 @@ def native_arm(workload, steps, warmup, a, rank, world, local):
             else:
                 v = om.bm1.size * 1e-9 / sec_step; u = "GDOF*steps/s"
             out["cpu_baseline"] = {"value": v, "unit": u, "cores": os.cpu_count() or 1, "kind": "port",
-                                   "sample": f"{max(2, a.cpu_steps)} time steps of the cylinder Re=50 config with the numpy oracle (BLAS threads <= cores), extrapolated to the unit"}
+                                   "sample": f"{max(2, a.cpu_steps)} time steps of the 2-D cylinder Re=50 config with the numpy oracle (BLAS threads <= cores), "
+                                             "same algorithm (Jacobi-PCG + Schwarz/coarse FGMRES), converted to the unit"}
         except Exception as e:  # the baseline is a reported number, never the product path
             out["cpu_baseline"] = {"value": None, "unit": unit, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {e}"}
-    ctx.close()
     if dist is not None:
         dist.destroy_process_group()
     return out

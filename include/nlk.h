@@ -91,13 +91,15 @@ typedef struct {
   int32_t cg_maxit;        /* Helmholtz CG cap */
   int32_t gmres_maxit;     /* Nek: 100 */
   int32_t lgmres;          /* SIZE lgmres = 30 */
-  int32_t precond;         /* 0 = mass-scaled identity, 1 = Schwarz + coarse (semg_xxt analogue) */
+  int32_t precond;         /* 0 = mass-scaled identity, 1 = Schwarz + coarse (semg_xxt analogue; dense inverse up to 5000
+                              vertices, sparse CSR + Jacobi-PCG above), 2 = Schwarz only, 3 = coarse only, 4 = Schwarz + sparse coarse */
   int32_t pr_proj;         /* residualProj: size of the pressure projection space (0 = off, Nek mxprev=20) */
   double cfl_limit;        /* 0.5 for the linear solver (src/linops/exponential_propagator.f90:12) */
   int32_t rst_mode;        /* 0 (default) = restart-field arithmetic exactly as written in src/vectors/real_vectors.f90:186-200
                               (rst slots receive alpha * the CURRENT fields of the other vector);
                               1 = consistent combination of the rst fields; 2 = matvec ignores input rst fields.
                               1/2 are NOT the reference behaviour; they exist to document its effect */
+  int32_t coarse_iters;    /* Jacobi-PCG iterations of the sparse coarse solve used above 5000 vertices (crs_solve analogue) */
 } nlk_params;
 
 int nlk_params_default(nlk_params* p);
@@ -154,6 +156,9 @@ int nlk_exptA_set_tau(nlk_op* op, double tau);                        /* apply_e
 int nlk_exptA_matvec(nlk_op* op, const nlk_vec* in, nlk_vec* out);
 int nlk_exptA_rmatvec(nlk_op* op, const nlk_vec* in, nlk_vec* out);
 int nlk_exptA_stats(const nlk_op* op, nlk_stats* out);
+/* bench hook: start from `in` (history reset as at the top of exptA_matvec), run nwarm untimed + nsteps timed perturbation
+ * time steps (body of the loop at exponential_propagator.f90:39-46) and return the device time of the timed ones */
+int nlk_exptA_time_steps(nlk_op* op, const nlk_vec* in, int32_t nwarm, int32_t nsteps, double* ms_timed);
 /* neklab_forcing registry (src/neklab_nek_forcing.f90:57-114): constant body force added to the perturbation rhs */
 int nlk_ctx_set_forcing(nlk_ctx* c, const double* fx, const double* fy, const double* fz);
 

@@ -40,7 +40,7 @@ class Params(C.Structure):
                 ("ptol", C.c_double), ("ifheat", C.c_int32), ("conductivity", C.c_double), ("rhocp", C.c_double),
                 ("ttol", C.c_double), ("buoyancy", C.c_double * 3), ("filter_weight", C.c_double),
                 ("filter_cutoff", C.c_double), ("cg_maxit", C.c_int32), ("gmres_maxit", C.c_int32), ("lgmres", C.c_int32),
-                ("precond", C.c_int32), ("pr_proj", C.c_int32), ("cfl_limit", C.c_double), ("rst_mode", C.c_int32)]
+                ("precond", C.c_int32), ("pr_proj", C.c_int32), ("cfl_limit", C.c_double), ("rst_mode", C.c_int32), ("coarse_iters", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -56,7 +56,7 @@ nlk_mesh_field nlk_mesh_neighbor nlk_mesh_basis nlk_dense_eig nlk_params_default
 nlk_ctx_set_dt nlk_comm_unique_id nlk_ctx_comm_init nlk_ctx_sync nlk_ctx_stream nlk_vec_create nlk_vec_destroy nlk_vec_copy nlk_vec_zero
 nlk_vec_rand nlk_vec_scal nlk_vec_axpby nlk_vec_dot nlk_vec_norm nlk_vec_size nlk_vec_save_rst nlk_vec_get_rst nlk_vec_nrst
 nlk_vec_clear_rst nlk_vec_upload nlk_vec_download nlk_basis_innerprod nlk_basis_axpy nlk_basis_dgs nlk_exptA_create
-nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_ctx_set_forcing
+nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_exptA_time_steps nlk_ctx_set_forcing
 nlk_eigs nlk_svds nlk_gmres nlk_test_axhelm nlk_test_dssum nlk_test_opdiv nlk_test_opgradt nlk_test_cdabdtp nlk_test_convect
 nlk_test_convect_adj nlk_test_helmholtz nlk_test_pressure nlk_test_precond nlk_test_cfl nlk_bench_kernel""".split()
 
@@ -360,6 +360,11 @@ class exptA_linop:
     def rmatvec(self, vec_in, vec_out=None):
         vec_out = vec_out or nek_dvector(self.ctx)
         _chk(lib().nlk_exptA_rmatvec(self.h, vec_in.h, vec_out.h)); return vec_out
+
+    def time_steps(self, vec_in, nwarm, nsteps):
+        ms = C.c_double()
+        _chk(lib().nlk_exptA_time_steps(self.h, vec_in.h, C.c_int32(nwarm), C.c_int32(nsteps), C.byref(ms)))
+        return ms.value
 
     def stats(self):
         s = Stats(); _chk(lib().nlk_exptA_stats(self.h, C.byref(s)))

@@ -196,7 +196,7 @@ static int ctx_setup(nlk_ctx* c) {
     c->have_schwarz = true;
     // coarse operator A0 = R0 E R0^T, column by column on the device; dense inverse on the host
     const int64_t nvt = hm.nvert;
-    if (nvt <= 5000 && c->prm.precond != 2) {
+    if (nvt <= 5000 && c->prm.precond != 2 && c->prm.precond != 4) {
       if (dev_alloc(c, &c->crs_part, (size_t)hm.E << d) || dev_alloc(c, &c->crs_r, nvt) || dev_alloc(c, &c->crs_y, nvt)) return 1;
       double* dA0 = nullptr; if (dev_alloc(c, &dA0, (size_t)nvt * nvt)) return 1;
       for (int64_t v = 0; v < nvt; ++v) {
@@ -221,6 +221,9 @@ static int ctx_setup(nlk_ctx* c) {
       NLK_CUDA(cudaMemcpyAsync(dA0, A0.data(), A0.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
       NLK_CUDA(cudaStreamSynchronize(c->st));
       c->have_coarse = true;
+    } else if (c->prm.precond != 2) {
+      c->crs_iters = c->prm.coarse_iters;
+      if (coarse_setup_sparse(c)) return 1;
     }
   }
   NLK_CUDA(cudaStreamSynchronize(c->st));
@@ -234,7 +237,7 @@ int nlk_params_default(nlk_params* p) {
   std::memset(p, 0, sizeof(*p));
   p->viscosity = 1.0; p->density = 1.0; p->torder = 3; p->vtol = 1e-9; p->ptol = 1e-7; p->ifheat = 0; p->conductivity = 1.0; p->rhocp = 1.0;
   p->ttol = 1e-9; p->filter_weight = 0.0; p->filter_cutoff = 1.0; p->cg_maxit = 1000; p->gmres_maxit = 100; p->lgmres = 30; p->precond = 1;
-  p->pr_proj = 0; p->cfl_limit = 0.5; p->rst_mode = 0;
+  p->pr_proj = 0; p->cfl_limit = 0.5; p->rst_mode = 0; p->coarse_iters = 12;
   return 0;
 }
 
@@ -512,6 +515,25 @@ extern "C" {
 int nlk_exptA_init(nlk_op* op) { if (push_baseflow(op)) return 1; return step_setup(op->c, op->tau, false); }
 int nlk_exptA_matvec(nlk_op* op, const nlk_vec* in, nlk_vec* out) { return exptA_apply(op, in, out, false); }
 int nlk_exptA_rmatvec(nlk_op* op, const nlk_vec* in, nlk_vec* out) { return exptA_apply(op, in, out, true); }
+int nlk_exptA_time_steps(nlk_op* op, const nlk_vec* in, int32_t nwarm, int32_t nsteps, double* ms_timed) {
+  nlk_ctx* c = op->c;
+  if (push_baseflow(op)) return 1;
+  if (step_setup(c, op->tau, false)) return 1;
+  if (state_from_vec(c, in->v, in->pr, in->theta)) return 1;
+  if (reset_history_pub(c)) return 1;
+  for (int i = 1; i <= nwarm; ++i) if (step_advance(c, i)) return 1;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  long l0 = g_launches; long cg0 = c->cg_iters, gm0 = c->gmres_iters, st0 = c->steps;
+  cudaEventRecord(e0, c->st);
+  for (int i = nwarm + 1; i <= nwarm + nsteps; ++i) if (step_advance(c, i)) return 1;
+  cudaEventRecord(e1, c->st);
+  NLK_CUDA(cudaStreamSynchronize(c->st));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_timed = ms;
+  op->stats.nsteps = c->nsteps; op->stats.dt = c->dt; op->stats.ms_total = ms; op->stats.launches = g_launches - l0;
+  op->stats.cg_iters = c->cg_iters - cg0; op->stats.gmres_iters = c->gmres_iters - gm0; op->stats.steps = c->steps - st0;
+  return 0;
+}
 int nlk_exptA_stats(const nlk_op* op, nlk_stats* out) { *out = op->stats; out->nsteps = op->c->nsteps; out->dt = op->c->dt; return 0; }
 
 // ============================================================================================== test hooks

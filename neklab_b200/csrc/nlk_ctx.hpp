@@ -79,6 +79,10 @@ struct nlk_ctx {
   double* sw_w = nullptr, *sw_z = nullptr, *sw_t = nullptr;   // Schwarz work (N1)
   double* crs_part = nullptr, *crs_r = nullptr, *crs_y = nullptr;
   bool have_coarse = false, have_schwarz = false;
+  // sparse coarse operator (large vertex counts): CSR of R0 E R0^T + Jacobi-PCG work vectors, all device-resident
+  bool coarse_sparse = false; int crs_iters = 0; int64_t crs_nnz = 0;
+  int32_t* crs_rowptr = nullptr; int32_t* crs_col = nullptr; double* crs_val = nullptr; double* crs_dinv = nullptr;
+  double* crs_p = nullptr, *crs_q = nullptr, *crs_z = nullptr, *crs_rr = nullptr, *crs_scal = nullptr;
   // pressure projection (residualProj)
   double* proj_X = nullptr, *proj_EX = nullptr, *proj_w = nullptr, *proj_xbar = nullptr; int nproj = 0;
   // time stepping
@@ -119,6 +123,8 @@ int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* it
 int apply_E(nlk_ctx* c, const double* p, double* ep, const double* out_mul);
 int apply_precond(nlk_ctx* c, const double* r, double* z, const double* in_mul);
 int pressure_solve_projected(nlk_ctx* c, double* rhs, double tol, double* x, int* iters);
+int coarse_setup_sparse(nlk_ctx* c);
+int coarse_solve_sparse(nlk_ctx* c, const double* rc, double* yc);
 int ortho(nlk_ctx* c, double* p);
 int reset_history_pub(nlk_ctx* c);
 void make_filter_matrix(const Basis& b, double w, double cutoff, std::vector<double>& F);

@@ -43,6 +43,7 @@ struct HostMesh {
   std::vector<int64_t> lglel;              // local -> global element (0-based)
   std::vector<double> xyz[3];
   std::vector<int64_t> vertex_local;       // E*nv (global vertex ids, 1-based)
+  std::vector<int64_t> vertex_all;         // Eg*nv (all elements; coarse-operator sparsity and colouring)
   std::vector<std::array<char, 3>> cbc_v, cbc_t;
   bool has_tbc = false;
   // geometry (all element-major, np1/np2/npd per element)

@@ -83,6 +83,7 @@ int build_mesh(HostMesh& hm, int ndim, int lx1, int lxd, int64_t nelg, int64_t n
   const int64_t E = nel;
   const double* xin[3] = {xm1, ym1, zm1};
   for (int c = 0; c < d; ++c) { if (!xin[c]) { set_error("missing coordinate array"); return 1; } hm.xyz[c].assign(xin[c], xin[c] + (size_t)E * np1); }
+  hm.vertex_all.assign(vertex_all, vertex_all + (size_t)nelg * nv);
   hm.vertex_local.resize((size_t)E * nv);
   for (int64_t e = 0; e < E; ++e) for (int c = 0; c < nv; ++c) hm.vertex_local[e * nv + c] = vertex_all[hm.lglel[e] * nv + c];
   hm.cbc_v.resize((size_t)E * nf); hm.cbc_t.resize((size_t)E * nf); hm.has_tbc = cbc_t != nullptr;

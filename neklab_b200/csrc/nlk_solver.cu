@@ -174,7 +174,8 @@ int apply_precond(nlk_ctx* c, const double* r, double* z, const double* in_mul) 
   if (c->have_coarse) {
     launch_coarse_restrict(dm, r, in_mul, c->crs_part, c->crs_r, c->st);
     if (ctx_allreduce(c, c->crs_r, (int)dm.nvert, false)) return 1;
-    launch_gemv(dm.A0inv, c->crs_r, c->crs_y, (int)dm.nvert, c->st);
+    if (c->coarse_sparse) { if (coarse_solve_sparse(c, c->crs_r, c->crs_y)) return 1; }
+    else launch_gemv(dm.A0inv, c->crs_r, c->crs_y, (int)dm.nvert, c->st);
     launch_coarse_prolong_add(dm, c->crs_y, z, 1, c->st);
   }
   return 0;

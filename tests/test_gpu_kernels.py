@@ -120,3 +120,27 @@ def test_pressure_gmres(case):
     nrm = lambda a: float(np.sqrt((a * a / om.bm2).sum() / om.volvm2))
     assert nrm(ops.ortho(om, res)) < 2e-10
     assert it < 600
+
+
+def test_sparse_coarse_level(nlk_lib):
+    """precond=4 forces the sparse (coloured-probing CSR + device Jacobi-PCG) coarse level used above 5000 vertices;
+    with enough inner iterations it must reproduce the dense-inverse preconditioner (up to a constant when E is singular)
+    and FGMRES must converge in a comparable number of iterations."""
+    from neklab_b200 import api
+    for name in ("box2d_n6", "box3d_n5", "box3d_n8_per"):
+        om, _, _ = box_case(**CASES[name])
+        m = nlk_mesh(om)
+        r = np.random.default_rng(11).standard_normal(om.bm2.shape)
+        r = ops.ortho(om, r) if not om.has_outflow else r
+        c1 = api.Context(m, api.default_params(viscosity=0.02, precond=1, gmres_maxit=600))
+        c4 = api.Context(m, api.default_params(viscosity=0.02, precond=4, gmres_maxit=600, coarse_iters=400))
+        z1 = ops.ortho(om, c1.precond(r)); z4 = ops.ortho(om, c4.precond(r))
+        assert rel(z4, z1) < 1e-6, name
+        u = [om.vmask[c] * x for c, x in enumerate(smooth_fields(om, om.ndim, 10))]
+        rhs = ops.ortho(om, -ops.opdiv(om, u))
+        c4.close()
+        c4 = api.Context(m, api.default_params(viscosity=0.02, precond=4, gmres_maxit=600, coarse_iters=40))
+        x1, it1 = c1.pressure(rhs, 1e-10); x4, it4 = c4.pressure(rhs, 1e-10)
+        assert rel(x4, x1) < 1e-7
+        assert it4 <= 3 * it1 + 20, (it1, it4)       # inexact (40-iteration) coarse solves cost outer iterations, not accuracy
+        c1.close(); c4.close()
