@@ -97,6 +97,12 @@ static int ctx_setup(nlk_ctx* c) {
   for (int k = 0; k < 8; ++k) if (dev_alloc(c, &c->wk[k], N1)) return 1;
   if (dev_alloc(c, &c->cg_x, N1) || dev_alloc(c, &c->cg_r, N1) || dev_alloc(c, &c->cg_p, N1) || dev_alloc(c, &c->cg_w, N1)) return 1;
   for (int k = 0; k < 5; ++k) if (dev_alloc(c, &c->pw[k], N2)) return 1;
+  // persistent cooperative PCG: single rank and small enough to be launch/latency-bound (NLK_NO_CGP=1 disables it)
+  c->use_cgp = hm.nranks <= 1 && N1 <= (size_t)1500000 && !getenv("NLK_NO_CGP");
+  if (c->use_cgp) {
+    for (int k = 0; k < d; ++k) if (dev_alloc(c, &c->cgm_x[k], N1) || dev_alloc(c, &c->cgm_p[k], N1) || dev_alloc(c, &c->cgm_w[k], N1)) return 1;
+    if (dev_alloc(c, &c->d_cg_iters, 4) || dev_alloc(c, &c->d_cg_total, 1)) return 1;
+  }
   if (dev_alloc(c, &c->gm_V, (size_t)(c->prm.lgmres + 1) * N2) || dev_alloc(c, &c->gm_Z, (size_t)c->prm.lgmres * N2)) return 1;
   if (dev_alloc(c, &c->sw_w, N1) || dev_alloc(c, &c->sw_z, N1) || dev_alloc(c, &c->sw_t, N1)) return 1;
   if (c->prm.pr_proj > 0) { if (dev_alloc(c, &c->proj_X, (size_t)c->prm.pr_proj * N2) || dev_alloc(c, &c->proj_EX, (size_t)c->prm.pr_proj * N2) || dev_alloc(c, &c->proj_w, N2) || dev_alloc(c, &c->proj_xbar, N2)) return 1; }
@@ -504,6 +510,7 @@ int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose) {
   }
   cudaEventRecord(e1, c->st);
   NLK_CUDA(cudaStreamSynchronize(c->st));
+  if (sync_cg_counter(c)) return 1;
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
   op->stats.nsteps = c->nsteps; op->stats.dt = c->dt; op->stats.ms_total = ms; op->stats.launches = g_launches - l0;
   op->stats.cg_iters = c->cg_iters - cg0; op->stats.gmres_iters = c->gmres_iters - gm0; op->stats.steps = c->steps - st0; op->stats.matvecs += 1;
@@ -528,6 +535,7 @@ int nlk_exptA_time_steps(nlk_op* op, const nlk_vec* in, int32_t nwarm, int32_t n
   for (int i = nwarm + 1; i <= nwarm + nsteps; ++i) if (step_advance(c, i)) return 1;
   cudaEventRecord(e1, c->st);
   NLK_CUDA(cudaStreamSynchronize(c->st));
+  if (sync_cg_counter(c)) return 1;
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
   *ms_timed = ms;
   op->stats.nsteps = c->nsteps; op->stats.dt = c->dt; op->stats.ms_total = ms; op->stats.launches = g_launches - l0;
@@ -586,7 +594,12 @@ int nlk_test_convect_adj(nlk_ctx* c, const double* const* U, const double* const
 int nlk_test_helmholtz(nlk_ctx* c, const double* f, double h1, double h2, int32_t comp, double tol, double* x, int32_t* iters) {
   if (up(c, c->wk[7], f, c->dm.N1)) return 1;
   int it = 0;
-  if (helmholtz_solve(c, c->wk[7], h1, h2, c->dm.mask[comp], tol, c->cg_x, &it)) return 1;
+  if (c->use_cgp) {                               // persistent cooperative path (small single-rank problems)
+    NLK_CUDA(cudaMemsetAsync(c->cg_x, 0, c->dm.N1 * sizeof(double), c->st));
+    double* rhs[1] = {c->wk[7]}; const double* mk[1] = {c->dm.mask[comp]}; double* sol[1] = {c->cg_x};
+    if (helmholtz_solve_multi(c, 1, rhs, h1, h2, mk, tol, sol)) return 1;
+    if (c->use_cgp) { NLK_CUDA(cudaMemcpyAsync(&it, c->d_cg_iters, sizeof(int), cudaMemcpyDeviceToHost, c->st)); NLK_CUDA(cudaStreamSynchronize(c->st)); }
+  } else if (helmholtz_solve(c, c->wk[7], h1, h2, c->dm.mask[comp], tol, c->cg_x, &it)) return 1;
   if (iters) *iters = it;
   return down(c, x, c->cg_x, c->dm.N1);
 }

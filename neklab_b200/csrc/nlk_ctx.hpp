@@ -74,6 +74,8 @@ struct nlk_ctx {
   // work
   double* wk[8] = {nullptr};             // N1 each
   double* cg_x = nullptr, *cg_r = nullptr, *cg_p = nullptr, *cg_w = nullptr;
+  double* cgm_x[3] = {nullptr}, *cgm_p[3] = {nullptr}, *cgm_w[3] = {nullptr};   // persistent multi-component PCG
+  int* d_cg_iters = nullptr; unsigned long long* d_cg_total = nullptr; unsigned long long cg_total_seen = 0; bool use_cgp = false;
   double* pw[6] = {nullptr};             // N2 each
   double* gm_V = nullptr, *gm_Z = nullptr;   // (lgmres+1) x N2, lgmres x N2
   double* sw_w = nullptr, *sw_z = nullptr, *sw_t = nullptr;   // Schwarz work (N1)
@@ -119,6 +121,8 @@ int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose);
 int step_setup(nlk_ctx* c, double tau, bool transpose);
 int step_advance(nlk_ctx* c, int istep);
 int helmholtz_solve(nlk_ctx* c, double* rhs_local, double h1, double h2, const double* mask, double tol, double* x, int* iters);
+int helmholtz_solve_multi(nlk_ctx* c, int nf, double* const* rhs_local, double h1, double h2, const double* const* masks, double tol, double* const* sol);
+int sync_cg_counter(nlk_ctx* c);
 int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* iters);
 int apply_E(nlk_ctx* c, const double* p, double* ep, const double* out_mul);
 int apply_precond(nlk_ctx* c, const double* r, double* z, const double* in_mul);

@@ -77,6 +77,17 @@ struct Reducer {          // scratch for deterministic two-stage reductions
   int maxblocks;
 };
 
+// persistent cooperative PCG (nlk_cgp.cu)
+struct CgField { double* x; double* r; double* p; double* w; const double* mask; double* sol; };
+struct CgArgs {
+  CgField f[3]; int nf;
+  const double *G, *bm1, *D, *diagA, *diagB, *mult, *binv;
+  const int32_t *gs_off, *gs_idx; int ngs; int64_t E;
+  double h1, h2, tol, vol; int maxit;
+  double* partial; int* iters_out; unsigned long long* iters_total;
+};
+bool launch_cg_persistent(const DevMesh& dm, CgArgs& a, cudaStream_t st);
+
 // ---- launch wrappers (all asynchronous on `st`) -------------------------------------------------------
 // K1  axhelm (hmholtz.f): w = h1*(D^T G D)u + h2*B u, element-local.  If pz != nullptr the CG direction update
 //     p = r*dinv + beta*p is fused in front (u is then p, read-modify-write), with dinv = 1/(h1*diagA+h2*diagB).

@@ -216,6 +216,35 @@ int helmholtz_solve(nlk_ctx* c, double* rhs, double h1, double h2, const double*
   return 0;
 }
 
+// all components of one Helmholtz system at once: persistent cooperative kernel when the problem is small and single-rank,
+// else the streamed per-component solver.  sol[k] += (h1 A + h2 B)^-1 mask dssum(rhs[k]); rhs arrays are overwritten.
+int helmholtz_solve_multi(nlk_ctx* c, int nf, double* const* rhs, double h1, double h2, const double* const* masks, double tol, double* const* sol) {
+  const DevMesh& dm = c->dm;
+  if (c->use_cgp && c->nccl.nranks <= 1) {
+    CgArgs a{};
+    for (int k = 0; k < nf; ++k) a.f[k] = CgField{c->cgm_x[k], rhs[k], c->cgm_p[k], c->cgm_w[k], masks[k], sol[k]};
+    a.nf = nf; a.G = dm.G; a.bm1 = dm.bm1; a.D = dm.D; a.diagA = dm.diagA; a.diagB = dm.diagB; a.mult = dm.vmult; a.binv = dm.binvm1;
+    a.gs_off = dm.gs_off; a.gs_idx = dm.gs_idx; a.ngs = dm.ngs; a.E = dm.E; a.h1 = h1; a.h2 = h2; a.tol = tol; a.vol = dm.volvm1;
+    a.maxit = c->prm.cg_maxit; a.partial = c->red.partial; a.iters_out = c->d_cg_iters; a.iters_total = c->d_cg_total;
+    if (launch_cg_persistent(dm, a, c->st)) return 0;
+    c->use_cgp = false;                       // cooperative launch unavailable: fall back for good
+  }
+  for (int k = 0; k < nf; ++k) {
+    if (helmholtz_solve(c, rhs[k], h1, h2, masks[k], tol, c->cg_x, nullptr)) return 1;
+    launch_lin(sol[k], dm.N1, 1.0, sol[k], 1.0, c->cg_x, 0, nullptr, 0, nullptr, nullptr, c->st);
+  }
+  return 0;
+}
+// fold the device-side iteration counter of the persistent PCG into the host statistics (one small D2H copy)
+int sync_cg_counter(nlk_ctx* c) {
+  if (!c->d_cg_total) return 0;
+  unsigned long long v = 0;
+  NLK_CUDA(cudaMemcpyAsync(&v, c->d_cg_total, sizeof(v), cudaMemcpyDeviceToHost, c->st));
+  NLK_CUDA(cudaStreamSynchronize(c->st));
+  c->cg_iters += (long)(v - c->cg_total_seen); c->cg_total_seen = v;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ pressure FGMRES (uzawa_gmres)
 int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* iters) {
   const DevMesh& dm = c->dm;
@@ -428,10 +457,10 @@ int step_advance(nlk_ctx* c, int istep) {
     launch_axhelm(dm, c->vp[k], c->wk[6], h1, h2, st);
     launch_lin(gp.p[k], dm.N1, 1.0, gp.p[k], 1.0, c->bf[k], -1.0, c->wk[6], 0, nullptr, nullptr, st);                           // res = Dtp* + bf - H u
   }
-  // ophinv: component-wise Jacobi-PCG
-  for (int k = 0; k < d; ++k) {
-    if (helmholtz_solve(c, gp.p[k], h1, h2, dm.mask[k], P.vtol, c->cg_x, nullptr)) return 1;
-    launch_lin(c->vp[k], dm.N1, 1.0, c->vp[k], 1.0, c->cg_x, 0, nullptr, 0, nullptr, nullptr, st);
+  // ophinv: Jacobi-PCG on every component (one persistent launch for all of them when the problem is small)
+  {
+    double* rhsv[3] = {gp.p[0], gp.p[1], gp.p[2]}; const double* mk[3] = {dm.mask[0], dm.mask[1], dm.mask[2]}; double* solv[3] = {c->vp[0], c->vp[1], c->vp[2]};
+    if (helmholtz_solve_multi(c, d, rhsv, h1, h2, mk, P.vtol, solv)) return 1;
   }
   // incomprp: E dp = -(bd1/dt) D u*, solved in the dt/bd1-scaled form (rhs = -D u*, dp = x * bd1/dt)
   double* rhs = c->pw[4];
@@ -452,8 +481,8 @@ int step_advance(nlk_ctx* c, int istep) {
     launch_lin(c->tp, dm.N1, 1.0, c->tp, 0, nullptr, 0, nullptr, 0, nullptr, dm.mask[3], st);                                   // bcdirsc (homogeneous)
     launch_axhelm(dm, c->tp, c->wk[6], h1t, h2t, st);
     launch_lin(c->wk[7], dm.N1, 1.0, c->bq, -1.0, c->wk[6], 0, nullptr, 0, nullptr, nullptr, st);
-    if (helmholtz_solve(c, c->wk[7], h1t, h2t, dm.mask[3], P.ttol, c->cg_x, nullptr)) return 1;
-    launch_lin(c->tp, dm.N1, 1.0, c->tp, 1.0, c->cg_x, 0, nullptr, 0, nullptr, nullptr, st);
+    { double* rhst[1] = {c->wk[7]}; const double* mk[1] = {dm.mask[3]}; double* solt[1] = {c->tp};
+      if (helmholtz_solve_multi(c, 1, rhst, h1t, h2t, mk, P.ttol, solt)) return 1; }
   }
   // ---- q_filter (param(103) > 0)
   if (P.filter_weight > 0 && c->filterF) {
