@@ -133,6 +133,15 @@ int nlk_vec_clear_rst(nlk_vec* v);                                   /* dclear_r
 int nlk_vec_upload(nlk_vec* v, const double* vx, const double* vy, const double* vz, const double* pr, const double* theta);
 int nlk_vec_download(const nlk_vec* v, double* vx, double* vy, double* vz, double* pr, double* theta);
 
+/* nek_zvector (src/vectors/neklab_vectors.f90:219-237; src/vectors/complex_vectors.f90:72-110): a complex vector is the
+ * pair (re, im) of nek_dvector handles; the three non-trivial TBPs are provided fused (no scratch copy of the vector,
+ * unlike nek_zscal/nek_zaxpby which deep-copy a temporary). */
+int nlk_zvec_scal(nlk_vec* re, nlk_vec* im, double alpha_re, double alpha_im);                       /* nek_zscal  :72-80  */
+int nlk_zvec_axpby(double alpha_re, double alpha_im, const nlk_vec* xre, const nlk_vec* xim,
+                   double beta_re, double beta_im, nlk_vec* sre, nlk_vec* sim);                        /* nek_zaxpby :82-98  */
+int nlk_zvec_dot(const nlk_vec* sre, const nlk_vec* sim, const nlk_vec* xre, const nlk_vec* xim,
+                 double* out_re, double* out_im);                                                      /* nek_zdot   :100-110: conj(self).x */
+
 /* block kernels replacing LightKrylov innerprod / linear_combination / double_gram_schmidt_step */
 int nlk_basis_innerprod(nlk_vec* const* X, int32_t k, const nlk_vec* y, double* h);
 int nlk_basis_axpy(nlk_vec* y, nlk_vec* const* X, int32_t k, const double* c);   /* y += X c (current fields; rst per quirk) */

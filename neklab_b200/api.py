@@ -55,7 +55,7 @@ SYMBOLS = """nlk_last_error nlk_version nlk_partition nlk_mesh_create nlk_mesh_d
 nlk_mesh_field nlk_mesh_neighbor nlk_mesh_basis nlk_dense_eig nlk_params_default nlk_ctx_create nlk_ctx_destroy nlk_ctx_set_tol
 nlk_ctx_set_dt nlk_comm_unique_id nlk_ctx_comm_init nlk_ctx_sync nlk_ctx_stream nlk_vec_create nlk_vec_destroy nlk_vec_copy nlk_vec_zero
 nlk_vec_rand nlk_vec_scal nlk_vec_axpby nlk_vec_dot nlk_vec_norm nlk_vec_size nlk_vec_save_rst nlk_vec_get_rst nlk_vec_nrst
-nlk_vec_clear_rst nlk_vec_upload nlk_vec_download nlk_basis_innerprod nlk_basis_axpy nlk_basis_dgs nlk_exptA_create
+nlk_vec_clear_rst nlk_vec_upload nlk_vec_download nlk_zvec_scal nlk_zvec_axpby nlk_zvec_dot nlk_basis_innerprod nlk_basis_axpy nlk_basis_dgs nlk_exptA_create
 nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_exptA_time_steps nlk_ctx_set_forcing
 nlk_eigs nlk_svds nlk_gmres nlk_test_axhelm nlk_test_dssum nlk_test_opdiv nlk_test_opgradt nlk_test_cdabdtp nlk_test_convect
 nlk_test_convect_adj nlk_test_helmholtz nlk_test_pressure nlk_test_precond nlk_test_cfl nlk_bench_kernel""".split()
@@ -340,6 +340,45 @@ class nek_dvector:
             self.h = None
         except Exception:
             pass
+
+
+class nek_zvector:
+    """`nek_zvector` (src/vectors/neklab_vectors.f90:219-237): complex vector as a (re, im) pair of `nek_dvector`."""
+
+    def __init__(self, ctx: "Context", re: nek_dvector | None = None, im: nek_dvector | None = None):
+        self.ctx = ctx
+        self.re = re if re is not None else nek_dvector(ctx)
+        self.im = im if im is not None else nek_dvector(ctx)
+
+    def zero(self):
+        self.re.zero(); self.im.zero()
+
+    def scal(self, alpha: complex):
+        _chk(lib().nlk_zvec_scal(self.re.h, self.im.h, C.c_double(alpha.real), C.c_double(alpha.imag)))
+
+    def axpby(self, alpha: complex, vec: "nek_zvector", beta: complex):
+        _chk(lib().nlk_zvec_axpby(C.c_double(alpha.real), C.c_double(alpha.imag), vec.re.h, vec.im.h,
+                                  C.c_double(beta.real), C.c_double(beta.imag), self.re.h, self.im.h))
+
+    def dot(self, vec: "nek_zvector") -> complex:
+        a = C.c_double(); b = C.c_double()
+        _chk(lib().nlk_zvec_dot(self.re.h, self.im.h, vec.re.h, vec.im.h, C.byref(a), C.byref(b)))
+        return complex(a.value, b.value)
+
+    def get_size(self):
+        return self.re.get_size()          # complex_vectors.f90: size of one part
+
+
+def svds(A: "exptA_linop", nsv, kdim, tol=0.0, x0=None, want_vectors=False):
+    """LightKrylov `svds` as called at src/neklab_analysis.f90:136 (Golub-Kahan, device-resident U and V bases)."""
+    sig = np.zeros(nsv); res = np.zeros(nsv); nit = C.c_int32(); info = C.c_int32()
+    U = V = None; ua = va = None
+    if want_vectors:
+        U = [nek_dvector(A.ctx) for _ in range(nsv)]; V = [nek_dvector(A.ctx) for _ in range(nsv)]
+        ua = (C.c_void_p * nsv)(*[u.h for u in U]); va = (C.c_void_p * nsv)(*[v.h for v in V])
+    _chk(lib().nlk_svds(A.h, C.c_int32(nsv), C.c_int32(kdim), C.c_double(tol), x0.h if x0 is not None else None,
+                        _p(sig), _p(res), ua, va, C.byref(nit), C.byref(info)))
+    return dict(sigma=sig, resid=res, niter=nit.value, info=info.value, U=U, V=V)
 
 
 class exptA_linop:

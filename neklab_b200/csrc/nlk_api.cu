@@ -442,6 +442,42 @@ int nlk_vec_download(const nlk_vec* v, double* vx, double* vy, double* vz, doubl
   return 0;
 }
 
+// ---- nek_zvector (complex_vectors.f90): (re, im) pairs of nek_dvector; rst slots follow the real-vector rules
+static int z_fields(nlk_ctx* c, const nlk_vec* v, int slot, double* out[5], size_t n_out[5]) {
+  const DevMesh& dm = c->dm; int k = 0;
+  for (int f = 0; f < dm.ndim; ++f) { out[k] = slot < 0 ? v->v[f] : v->rv[slot][f]; n_out[k++] = dm.N1; }
+  out[k] = slot < 0 ? v->pr : v->rpr[slot]; n_out[k++] = dm.N2;
+  if (c->prm.ifheat) { out[k] = slot < 0 ? v->theta : v->rth[slot]; n_out[k++] = dm.N1; }
+  return k;
+}
+int nlk_zvec_scal(nlk_vec* re, nlk_vec* im, double ar, double ai) {
+  nlk_ctx* c = re->c;
+  if (re->nrst != im->nrst) { set_error("zscal: re/im carry different numbers of rst fields"); return 1; }
+  for (int slot = -1; slot < re->nrst; ++slot) {
+    double* R[5]; double* I[5]; size_t n[5];
+    int nf = z_fields(c, re, slot, R, n); z_fields(c, im, slot, I, n);
+    for (int f = 0; f < nf; ++f) {           // (re, im) <- (ar*re - ai*im, ar*im + ai*re), through one scratch field
+      double* t = n[f] == c->dm.N1 ? c->wk[0] : c->pw[0];
+      launch_lin(t, n[f], ar, R[f], -ai, I[f], 0, nullptr, 0, nullptr, nullptr, c->st);
+      launch_lin(I[f], n[f], ar, I[f], ai, R[f], 0, nullptr, 0, nullptr, nullptr, c->st);
+      NLK_CUDA(cudaMemcpyAsync(R[f], t, n[f] * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    }
+  }
+  return 0;
+}
+int nlk_zvec_axpby(double ar, double ai, const nlk_vec* xre, const nlk_vec* xim, double br, double bi, nlk_vec* sre, nlk_vec* sim) {
+  // self = alpha*x + beta*self (complex); the reference does zscal(beta) then adds alpha*x built in a scratch zvector
+  if (nlk_zvec_scal(sre, sim, br, bi)) return 1;
+  if (nlk_vec_axpby(ar, xre, 1.0, sre) || nlk_vec_axpby(-ai, xim, 1.0, sre)) return 1;
+  if (nlk_vec_axpby(ar, xim, 1.0, sim) || nlk_vec_axpby(ai, xre, 1.0, sim)) return 1;
+  return 0;
+}
+int nlk_zvec_dot(const nlk_vec* sre, const nlk_vec* sim, const nlk_vec* xre, const nlk_vec* xim, double* out_re, double* out_im) {
+  double a, b, cc, d;                          // conj(s).x = (sre.xre + sim.xim) + i (sre.xim - sim.xre)
+  if (nlk_vec_dot(sre, xre, &a) || nlk_vec_dot(sim, xim, &b) || nlk_vec_dot(sre, xim, &cc) || nlk_vec_dot(sim, xre, &d)) return 1;
+  *out_re = a + b; *out_im = cc - d; return 0;
+}
+
 // seeded, C0, BC-satisfying random vector (nek_drand: real_vectors.f90:52-123 -- random_number is compiler-specific,
 // so the generator is a documented replacement: smooth field + splitmix64 noise, then dssum*vmult, mask, normalise)
 int nlk_vec_rand(nlk_vec* v, int32_t ifnorm, uint64_t seed) {

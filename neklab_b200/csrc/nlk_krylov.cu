@@ -291,7 +291,20 @@ int nlk_svds(nlk_op* op, int32_t nsv, int32_t kdim, double tol, const nlk_vec* x
   }
   const int n = std::min(k, kdim);
   for (int j = 0; j < nsv && j < (int)sv.size(); ++j) { sigma[j] = sv[j]; resid[j] = res[j]; }
-  (void)Uout; (void)Vout;
+  // singular vectors: right v_j = V_n z_j (z_j eigenvector of B^T B), left u_j = U_n (B z_j) / sigma_j
+  if ((Uout || Vout) && n > 0) {
+    std::vector<double> BtB((size_t)n * n, 0.0), w(n), Z((size_t)n * n);
+    for (int i = 0; i < n; ++i) { BtB[(size_t)i * n + i] = alpha[i] * alpha[i] + (i > 0 ? beta[i] * beta[i] : 0.0); if (i + 1 < n) { BtB[(size_t)i * n + i + 1] = alpha[i] * beta[i + 1]; BtB[(size_t)(i + 1) * n + i] = alpha[i] * beta[i + 1]; } }
+    sym_eig_jacobi(n, BtB.data(), w.data(), Z.data());
+    for (int j = 0; j < nsv && j < n; ++j) {
+      const int src = n - 1 - j; const double sg = std::sqrt(std::max(w[src], 0.0));
+      std::vector<double> zc(n), uc(n);
+      for (int i = 0; i < n; ++i) zc[i] = Z[(size_t)i * n + src];
+      for (int i = 0; i < n; ++i) uc[i] = (alpha[i] * zc[i] + (i + 1 < n ? beta[i + 1] * zc[i + 1] : 0.0)) / (sg > 0 ? sg : 1.0);
+      if (Vout) { if (nlk_vec_zero(Vout[j]) || basis_axpy(c, Vout[j], V.data(), n, zc.data())) return 1; }
+      if (Uout) { if (nlk_vec_zero(Uout[j]) || basis_axpy(c, Uout[j], U.data(), n, uc.data())) return 1; }
+    }
+  }
   if (niter_out) *niter_out = n;
   if (conv < nsv) *info = 1;
   for (auto& x : U) nlk_vec_destroy(x);

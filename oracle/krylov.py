@@ -166,6 +166,7 @@ def svds(A, x0, nsv, kdim, tol=RTOL_DP):
         res = np.abs(b * P[n - 1, :])
         if n >= nsv and int((res < tol).sum()) >= nsv:
             break
+    svds.last_B = B                # the projected (bidiagonal) matrix of the final step, for singular-vector reconstruction
     return sig, res, U, V, k + 1
 
 

@@ -109,3 +109,35 @@ def test_cylinder_eigs_same_start_vector_as_oracle_golden(nlk_lib):
     ctx.close()
     assert r["info"] == 0
     assert abs(abs(r["lam"][0]) - gold["modulus"][0]) < 1e-6 * gold["modulus"][0], (abs(r["lam"][0]), gold["modulus"][0])
+
+
+def test_svds_vectors_and_zvector(small):
+    """singular vectors u = U p, v = V q of the projected bidiagonal matrix match the oracle's reconstruction (the reference's
+    A^T is a continuous adjoint fed with direct-run rst fields, so A v = sigma u only holds approximately -- in the oracle too);
+    nek_zvector arithmetic matches complex numpy."""
+    from neklab_b200 import api
+    om, ctx, A_or, A = small
+    x0 = seeded_field(om, 8)
+    sig_or, res_or, U, V, k_or = svds_or(A_or, x0, nsv=1, kdim=6, tol=1e-5)
+    P, s, Qt = np.linalg.svd(svds_or.last_B)
+    u_or = NekVec(om, 3); v_or = NekVec(om, 3)
+    for i in range(k_or):
+        v_or.axpby(Qt[0, i], V[i], 1.0); u_or.axpby(P[i, 0], U[i], 1.0)
+    xd = _dev(ctx, x0)
+    r = api.svds(A, nsv=1, kdim=6, tol=1e-5, x0=xd, want_vectors=True)
+    assert r["niter"] == k_or and abs(r["sigma"][0] - sig_or[0]) < 1e-8
+    for dev, ora in ((r["U"][0], u_or), (r["V"][0], v_or)):
+        v, _, _ = dev.download()
+        sgn = np.sign(float((v[0] * ora.v[0] * om.bm1).sum()))
+        assert rel(sgn * v[0], ora.v[0]) < 1e-6 and rel(sgn * v[1], ora.v[1]) < 1e-6
+        assert abs(dev.norm() - 1.0) < 1e-8
+    # nek_zvector
+    a = seeded_field(om, 31); b = seeded_field(om, 32); c_ = seeded_field(om, 33); d = seeded_field(om, 34)
+    z1 = api.nek_zvector(ctx, _dev(ctx, a), _dev(ctx, b)); z2 = api.nek_zvector(ctx, _dev(ctx, c_), _dev(ctx, d))
+    ref1 = [a.v[k] + 1j * b.v[k] for k in range(2)]; ref2 = [c_.v[k] + 1j * d.v[k] for k in range(2)]
+    dot_ref = sum(complex((np.conj(ref1[k]) * ref2[k] * om.bm1).sum()) for k in range(2))
+    assert abs(z1.dot(z2) - dot_ref) < 1e-12 * abs(dot_ref)
+    z1.axpby(0.3 - 0.7j, z2, 1.1 + 0.2j)
+    ref = [(0.3 - 0.7j) * ref2[k] + (1.1 + 0.2j) * ref1[k] for k in range(2)]
+    vr, _, _ = z1.re.download(); vi, _, _ = z1.im.download()
+    assert rel(vr[0], ref[0].real) < 1e-13 and rel(vi[1], ref[1].imag) < 1e-13
