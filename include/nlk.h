@@ -168,6 +168,15 @@ int nlk_exptA_stats(const nlk_op* op, nlk_stats* out);
 /* bench hook: start from `in` (history reset as at the top of exptA_matvec), run nwarm untimed + nsteps timed perturbation
  * time steps (body of the loop at exponential_propagator.f90:39-46) and return the device time of the timed ones */
 int nlk_exptA_time_steps(nlk_op* op, const nlk_vec* in, int32_t nwarm, int32_t nsteps, double* ms_timed);
+int nlk_exptA_set_baseflow(nlk_op* op, const nlk_vec* baseflow);      /* nek_jacobian%X = X (src/systems/neklab_systems.f90) */
+/* nek_system%response (src/systems/fixed_point.f90:4-40): out = F_tau(in) - in with the NONLINEAR stepper
+ * (Nek `fluid`/`plan3`: makef/advab, cresvif, ophinv, incomprn), dt from the CFL of `in` at cfl_limit (0.4 in the reference) */
+int nlk_nonlinear_map(nlk_ctx* c, double tau, double cfl_limit, const nlk_vec* in, nlk_vec* out);
+/* newton_fixed_point_iteration (src/neklab_analysis.f90:158-212) with gmres on nek_jacobian = exptA - I
+ * (src/systems/fixed_point.f90:42-96) and the tolerance schedulers nek_constant_tol / nek_dynamic_tol
+ * (src/systems/neklab_systems.f90:229-335; tol_mode 1 / 2).  X is updated in place; rnorm_hist gets niter+1 values. */
+int nlk_newton_fixed_point(nlk_ctx* c, double tau, nlk_vec* X, double tol, int32_t tol_mode, int32_t maxiter, int32_t gmres_kdim,
+                           double* rnorm_hist, int32_t* niter, int32_t* info);
 /* neklab_forcing registry (src/neklab_nek_forcing.f90:57-114): constant body force added to the perturbation rhs */
 int nlk_ctx_set_forcing(nlk_ctx* c, const double* fx, const double* fy, const double* fz);
 

@@ -56,7 +56,7 @@ nlk_mesh_field nlk_mesh_neighbor nlk_mesh_basis nlk_dense_eig nlk_params_default
 nlk_ctx_set_dt nlk_comm_unique_id nlk_ctx_comm_init nlk_ctx_sync nlk_ctx_stream nlk_vec_create nlk_vec_destroy nlk_vec_copy nlk_vec_zero
 nlk_vec_rand nlk_vec_scal nlk_vec_axpby nlk_vec_dot nlk_vec_norm nlk_vec_size nlk_vec_save_rst nlk_vec_get_rst nlk_vec_nrst
 nlk_vec_clear_rst nlk_vec_upload nlk_vec_download nlk_zvec_scal nlk_zvec_axpby nlk_zvec_dot nlk_basis_innerprod nlk_basis_axpy nlk_basis_dgs nlk_exptA_create
-nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_exptA_time_steps nlk_ctx_set_forcing
+nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_exptA_time_steps nlk_exptA_set_baseflow nlk_nonlinear_map nlk_newton_fixed_point nlk_ctx_set_forcing
 nlk_eigs nlk_svds nlk_gmres nlk_test_axhelm nlk_test_dssum nlk_test_opdiv nlk_test_opgradt nlk_test_cdabdtp nlk_test_convect
 nlk_test_convect_adj nlk_test_helmholtz nlk_test_pressure nlk_test_precond nlk_test_cfl nlk_bench_kernel""".split()
 
@@ -416,6 +416,21 @@ class exptA_linop:
             self.h = None
         except Exception:
             pass
+
+
+def nonlinear_map(ctx: Context, tau, vec_in: nek_dvector, cfl_limit=0.4) -> nek_dvector:
+    """`nek_system%response` (src/systems/fixed_point.f90:4-40): F_tau(X) - X."""
+    out = nek_dvector(ctx)
+    _chk(lib().nlk_nonlinear_map(ctx.h, C.c_double(tau), C.c_double(cfl_limit), vec_in.h, out.h))
+    return out
+
+
+def newton_fixed_point_iteration(ctx: Context, bf: nek_dvector, tol, tau=1.0, tol_mode=1, maxiter=40, gmres_kdim=30):
+    """src/neklab_analysis.f90:158-212: Newton-GMRES for F_tau(X) = X; `bf` is updated in place."""
+    hist = np.zeros(maxiter + 2); nit = C.c_int32(); info = C.c_int32()
+    _chk(lib().nlk_newton_fixed_point(ctx.h, C.c_double(tau), bf.h, C.c_double(tol), C.c_int32(tol_mode), C.c_int32(maxiter),
+                                      C.c_int32(gmres_kdim), _p(hist), C.byref(nit), C.byref(info)))
+    return dict(residuals=hist[:nit.value + 1].copy(), niter=nit.value, info=info.value)
 
 
 def eigs(A: exptA_linop, nev, kdim, tol=0.0, transpose=False, x0=None, want_vectors=False, callback=None):

@@ -558,6 +558,66 @@ extern "C" {
 int nlk_exptA_init(nlk_op* op) { if (push_baseflow(op)) return 1; return step_setup(op->c, op->tau, false); }
 int nlk_exptA_matvec(nlk_op* op, const nlk_vec* in, nlk_vec* out) { return exptA_apply(op, in, out, false); }
 int nlk_exptA_rmatvec(nlk_op* op, const nlk_vec* in, nlk_vec* out) { return exptA_apply(op, in, out, true); }
+int nlk_exptA_set_baseflow(nlk_op* op, const nlk_vec* bf) { return nlk_vec_copy(op->baseflow, bf); }
+
+int nlk_nonlinear_map(nlk_ctx* c, double tau, double cfl_limit, const nlk_vec* in, nlk_vec* out) {
+  if (in == out) { set_error("nonlinear_map: vec_in and vec_out must differ"); return 1; }
+  c->nonlinear = true; c->adjoint = false;
+  int rc = 0;
+  do {
+    if ((rc = step_setup_cfl(c, tau, cfl_limit, CPtr3{{in->v[0], in->v[1], in->v[2]}}))) break;
+    if ((rc = state_from_vec(c, in->v, in->pr, in->theta))) break;
+    if ((rc = reset_history_pub(c))) break;
+    for (int istep = 1; istep <= c->nsteps && !rc; ++istep) rc = step_advance(c, istep);
+    if (rc) break;
+    if ((rc = copy_fields(c, out->v, out->pr, out->theta, c->vp, c->prp, c->tp))) break;
+    out->nrst = 0;
+    rc = nlk_vec_axpby(-1.0, in, 1.0, out);                       // vec_out%sub(vec_in)
+  } while (0);
+  c->nonlinear = false;
+  if (!rc) rc = sync_cg_counter(c);
+  return rc;
+}
+
+// LightKrylov `newton` with gmres_rdp on the fixed-point Jacobian and neklab's tolerance schedulers
+int nlk_newton_fixed_point(nlk_ctx* c, double tau, nlk_vec* X, double tol, int32_t tol_mode, int32_t maxiter, int32_t gmres_kdim,
+                           double* rnorm_hist, int32_t* niter, int32_t* info) {
+  const double mintol = 10.0 * 1e-15, maxtol = 1.0e-4;
+  const double vtol0 = c->prm.vtol, ptol0 = c->prm.ptol, cfl0 = c->prm.cfl_limit;
+  nlk_vec *r = nullptr, *dx = nullptr; nlk_op* J = nullptr;
+  if (nlk_vec_create(c, &r) || nlk_vec_create(c, &dx) || nlk_exptA_create(c, tau, X, &J)) return 1;
+  double tol_s = std::max(tol, mintol);
+  *info = 1; int it = 0; int rc = 0;
+  for (it = 0; it <= maxiter; ++it) {
+    // scheduler (nek_constant_tol | nek_dynamic_tol); the first evaluation uses the target tolerance
+    if (it > 0 && tol_mode == 2) {
+      double target = std::min(std::max(tol, mintol), maxtol);
+      double t = std::max(0.1 * rnorm_hist[it - 1], target);
+      if (t < 10 * target) t = target;
+      tol_s = std::min(t, maxtol);
+    }
+    c->prm.vtol = tol_s * 0.1; c->prm.ptol = tol_s * 0.1;          // nonlinear_map: vtol = ptol = atol*0.1
+    if ((rc = nlk_nonlinear_map(c, tau, 0.4, X, r))) break;
+    double rn; if ((rc = nlk_vec_norm(r, &rn))) break;
+    rnorm_hist[it] = rn;
+    if (rn < tol) { *info = 0; break; }
+    if (it == maxiter) break;
+    // Jacobian = exptA(X) - I with vtol = ptol = atol*0.5, cfl 0.5
+    c->prm.vtol = tol_s * 0.5; c->prm.ptol = tol_s * 0.5; c->prm.cfl_limit = 0.5;
+    if ((rc = nlk_exptA_set_baseflow(J, X))) break;
+    if ((rc = nlk_vec_zero(dx))) break;
+    int ginfo = 0;
+    if ((rc = nlk_gmres(J, 1, r, dx, gmres_kdim, tol_s, std::sqrt(1e-15), 10, 0, &ginfo))) break;
+    int nr = X->nrst; X->nrst = 0;
+    if ((rc = nlk_vec_axpby(-1.0, dx, 1.0, X))) break;             // X <- X - dX
+    X->nrst = nr;
+  }
+  *niter = it;
+  c->prm.vtol = vtol0; c->prm.ptol = ptol0; c->prm.cfl_limit = cfl0;
+  nlk_exptA_destroy(J); nlk_vec_destroy(r); nlk_vec_destroy(dx);
+  return rc;
+}
+
 int nlk_exptA_time_steps(nlk_op* op, const nlk_vec* in, int32_t nwarm, int32_t nsteps, double* ms_timed) {
   nlk_ctx* c = op->c;
   if (push_baseflow(op)) return 1;

@@ -88,7 +88,7 @@ struct nlk_ctx {
   // pressure projection (residualProj)
   double* proj_X = nullptr, *proj_EX = nullptr, *proj_w = nullptr, *proj_xbar = nullptr; int nproj = 0;
   // time stepping
-  double dt = 0; int nsteps = 0; bool adjoint = false;
+  double dt = 0; int nsteps = 0; bool adjoint = false; bool nonlinear = false;
   // statistics
   long cg_iters = 0, gmres_iters = 0, steps = 0;
 };
@@ -119,6 +119,7 @@ int ctx_read_scalars(nlk_ctx* c, int count);                              // d_r
 int vec_alloc_rst(nlk_vec* v, int slot);
 int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose);
 int step_setup(nlk_ctx* c, double tau, bool transpose);
+int step_setup_cfl(nlk_ctx* c, double tau, double cfl_limit, CPtr3 u);
 int step_advance(nlk_ctx* c, int istep);
 int helmholtz_solve(nlk_ctx* c, double* rhs_local, double h1, double h2, const double* mask, double tol, double* x, int* iters);
 int helmholtz_solve_multi(nlk_ctx* c, int nf, double* const* rhs_local, double h1, double h2, const double* const* masks, double tol, double* const* sol);

@@ -373,10 +373,12 @@ static void ab_coeffs(int nab, int nbd, double* ab) {       // Nek setabbd, cons
 
 // setup_nek (src/neklab_nek_setup.f90:193-224): dt = cfl_limit/ctarg, nsteps = ceiling(tau/dt), dt = tau/nsteps
 int step_setup(nlk_ctx* c, double tau, bool transpose) {
-  const DevMesh& dm = c->dm;
   c->adjoint = transpose;
+  return step_setup_cfl(c, tau, c->prm.cfl_limit, CPtr3{{c->U[0], c->U[1], c->U[2]}});
+}
+int step_setup_cfl(nlk_ctx* c, double tau, double cfl_limit, CPtr3 u) {
+  const DevMesh& dm = c->dm;
   if (tau <= 0) { set_error("invalid endtime (tau <= 0)"); return 1; }
-  CPtr3 u{{c->U[0], c->U[1], c->U[2]}};
   launch_cfl(dm, u, c->d_red, c->red, c->st);
   if (ctx_allreduce(c, c->d_red, 1, true)) return 1;
   if (ctx_read_scalars(c, 1)) return 1;
@@ -385,7 +387,7 @@ int step_setup(nlk_ctx* c, double tau, bool transpose) {
     if (c->dt <= 0) { set_error("zero base flow and no previous dt: cannot choose a time step"); return 1; }
     c->nsteps = (int)std::ceil(tau / c->dt - 1e-12);
   } else {
-    double dt = c->prm.cfl_limit / ctarg;
+    double dt = cfl_limit / ctarg;
     c->nsteps = (int)std::ceil(tau / dt);
     c->dt = tau / c->nsteps;
   }
@@ -425,7 +427,9 @@ int step_advance(nlk_ctx* c, int istep) {
   }
   CPtr3 Ub{{c->U[0], c->U[1], c->U[2]}}, up{{c->vp[0], c->vp[1], c->vp[2]}};
   Ptr4 bf4{{c->bf[0], c->bf[1], c->bf[2], nullptr}};
-  if (!c->adjoint) {
+  if (c->nonlinear) {
+    launch_convect(dm, CPtr4{{c->vp[0], c->vp[1], c->vp[2], nullptr}}, d, up, bf4, -rho, 1, st);  // advab: u.grad u (Nek plan3/makef)
+  } else if (!c->adjoint) {
     launch_convect(dm, CPtr4{{c->U[0], c->U[1], c->U[2], nullptr}}, d, up, bf4, -rho, 1, st);     // u'.grad U
     launch_convect(dm, CPtr4{{c->vp[0], c->vp[1], c->vp[2], nullptr}}, d, Ub, bf4, -rho, 1, st);  // U.grad u'
   } else {
@@ -437,6 +441,7 @@ int step_advance(nlk_ctx* c, int istep) {
   for (int k = 0; k < d; ++k) { t.bf[k] = c->bf[k]; t.e1[k] = c->exx1[k]; t.e2[k] = c->exx2[k]; t.u[k] = c->vp[k]; t.lag1[k] = c->vlag[0][k]; t.lag2[k] = c->vlag[1][k]; t.coef[k] = rho / dt; }
   if (P.ifheat) {
     if (c->adjoint) { set_error("adjoint Boussinesq step is out of scope (no reference config uses it)"); return 1; }
+    if (c->nonlinear) { set_error("nonlinear Boussinesq stepper (nek_system_temp) is out of scope this round"); return 1; }
     NLK_CUDA(cudaMemsetAsync(c->bq, 0, dm.N1 * sizeof(double), st));
     Ptr4 bq4{{c->bq, nullptr, nullptr, nullptr}};
     launch_convect(dm, CPtr4{{c->T, nullptr, nullptr, nullptr}}, 1, up, bq4, -P.rhocp, 1, st);    // u'.grad T
@@ -447,7 +452,8 @@ int step_advance(nlk_ctx* c, int istep) {
   launch_rhs_tail(dm, t, nf, ab[0], ab[1], ab[2], bd[1], bd[2], bd[3], st);
   // ---- igeom = 2: velocity.  cresvipp
   const double h1 = P.viscosity, h2 = rho * bd[0] / dt;
-  for (int k = 0; k < d; ++k) launch_lin(c->vp[k], dm.N1, 1.0, c->vp[k], 0, nullptr, 0, nullptr, 0, nullptr, dm.mask[k], st);   // bcdirvc (homogeneous)
+  if (!c->nonlinear)    // bcdirvc: homogeneous for perturbations; the nonlinear state keeps its (inflow) boundary values
+    for (int k = 0; k < d; ++k) launch_lin(c->vp[k], dm.N1, 1.0, c->vp[k], 0, nullptr, 0, nullptr, 0, nullptr, dm.mask[k], st);
   double* pext = c->pw[3];
   if (nbd == 3) launch_lin(pext, dm.N2, 2.0, c->prp, -1.0, c->prlag, 0, nullptr, 0, nullptr, nullptr, st);                    // extrapprp
   else NLK_CUDA(cudaMemcpyAsync(pext, c->prp, dm.N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));

@@ -273,6 +273,7 @@ class PertStepper:
         self.mesh, self.prm = mesh, prm
         self.d = mesh.ndim
         self.adjoint = False
+        self.nonlinear = False                               # ifpert = .false.: Nek `fluid`/`plan3` instead of `fluidp`
         self.U = [np.zeros_like(mesh.bm1) for _ in range(self.d)]
         self.T = np.zeros_like(mesh.bm1)
         self.forcing = None                                  # neklab_ffx/y/z (neklab_nek_forcing.f90:19-21)
@@ -365,8 +366,11 @@ class PertStepper:
             if self.forcing is not None:
                 f = f + self.forcing[c]
             bf.append(f * B)
-        # advabp / advabp_adjoint
-        if not self.adjoint:
+        # advab (nonlinear, Nek plan3/makef) | advabp / advabp_adjoint
+        if self.nonlinear:
+            for c in range(d):
+                bf[c] = bf[c] - rho * ops.convect_new(m, self.vp[c], self.vp)       # u.grad u_c
+        elif not self.adjoint:
             for c in range(d):
                 bf[c] = bf[c] - rho * ops.convect_new(m, self.U[c], self.vp)     # u'.grad U_c
                 bf[c] = bf[c] - rho * ops.convect_new(m, self.vp[c], self.U)     # U.grad u'_c
@@ -409,8 +413,9 @@ class PertStepper:
         # ---------------- igeom = 2 : velocity
         h1 = prm.viscosity
         h2 = rho * bd[0] / dt
-        # cresvipp (perturbation Dirichlet values are zero: bcdirvc == mask)
-        self.vp = [m.vmask[c] * self.vp[c] for c in range(d)]
+        # cresvipp (perturbation Dirichlet values are zero: bcdirvc == mask); cresvif keeps the inhomogeneous values
+        if not self.nonlinear:
+            self.vp = [m.vmask[c] * self.vp[c] for c in range(d)]
         if nbd == 3:
             pext = 2.0 * self.prp - self.prlag
         else:
@@ -560,6 +565,22 @@ def seeded_field(mesh: SEMesh, seed: int, ifheat=False, torder=3) -> NekVec:
         f = np.cos(0.5 * x[:, 0]) * np.sin(1.1 * x[:, 1]) + 0.1 * rng.standard_normal(mesh.bm1.shape)
         v.theta = mesh.tmask * (mesh.dssum(f) * mesh.vmult)
     return v
+
+
+# --------------------------------------------------------------------------- nonlinear flow map / Newton
+def nonlinear_map(st: PertStepper, x: NekVec, tau: float, cfl_limit: float = 0.4) -> NekVec:
+    """`nek_system%response` (src/systems/fixed_point.f90:4-40): F_tau(X) - X with the nonlinear stepper."""
+    st.nonlinear = True; st.adjoint = False
+    st.U = [v.copy() for v in x.v]                       # CFL of the state itself (setup_nonlinear_solver, recompute_dt)
+    st.setup(tau, cfl_limit, False)
+    st.set_state(x.v, x.pr, x.theta); st.reset_history()
+    for istep in range(1, st.nsteps + 1):
+        st.advance(istep)
+    out = NekVec(st.mesh, st.prm.torder, st.prm.ifheat)
+    out.v = [a.copy() for a in st.vp]; out.pr = st.prp.copy(); out.theta = st.tp.copy()
+    out.axpby(-1.0, x, 1.0)                              # vec_out%sub(vec_in)
+    st.nonlinear = False
+    return out
 
 
 # --------------------------------------------------------------------------- exptA
