@@ -54,7 +54,7 @@ def test_newton_cylinder(nlk_lib):
     ctx.close()
     ctx = api.Context(nlk_mesh(om), api.default_params(viscosity=1 / 45.0, **kw))
     X = ctx.vec(); X.upload(bf.v, bf.pr)
-    r = api.newton_fixed_point_iteration(ctx, X, tol=1e-6, tau=1.0, tol_mode=1, maxiter=8, gmres_kdim=30)
+    r = api.newton_fixed_point_iteration(ctx, X, tol=1e-6, tau=1.0, tol_mode=1, maxiter=3, gmres_kdim=30)
     v, _, _ = X.download()
     ctx.close()
     res = r["residuals"]
