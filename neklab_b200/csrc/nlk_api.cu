@@ -98,7 +98,7 @@ static int ctx_setup(nlk_ctx* c) {
   if (dev_alloc(c, &c->cg_x, N1) || dev_alloc(c, &c->cg_r, N1) || dev_alloc(c, &c->cg_p, N1) || dev_alloc(c, &c->cg_w, N1)) return 1;
   for (int k = 0; k < 5; ++k) if (dev_alloc(c, &c->pw[k], N2)) return 1;
   // persistent cooperative PCG: single rank and small enough to be launch/latency-bound (NLK_NO_CGP=1 disables it)
-  c->use_cgp = hm.nranks <= 1 && N1 <= (size_t)1500000 && !getenv("NLK_NO_CGP");
+  { size_t lim = 8000000; if (const char* e = getenv("NLK_CGP_MAX_POINTS")) lim = (size_t)atoll(e); c->use_cgp = hm.nranks <= 1 && N1 <= lim && !getenv("NLK_NO_CGP"); }
   if (c->use_cgp) {
     for (int k = 0; k < d; ++k) if (dev_alloc(c, &c->cgm_x[k], N1) || dev_alloc(c, &c->cgm_p[k], N1) || dev_alloc(c, &c->cgm_w[k], N1)) return 1;
     if (dev_alloc(c, &c->d_cg_iters, 4) || dev_alloc(c, &c->d_cg_total, 1)) return 1;
@@ -522,6 +522,7 @@ int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose) {
   nlk_ctx* c = op->c;
   if (in == out) { set_error("exptA: vec_in and vec_out must differ"); return 1; }
   const int nrst = c->prm.torder - 1;
+  if (sync_cg_counter(c)) return 1;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   long l0 = g_launches; long cg0 = c->cg_iters, gm0 = c->gmres_iters, st0 = c->steps;
   cudaEventRecord(e0, c->st);
@@ -625,6 +626,7 @@ int nlk_exptA_time_steps(nlk_op* op, const nlk_vec* in, int32_t nwarm, int32_t n
   if (state_from_vec(c, in->v, in->pr, in->theta)) return 1;
   if (reset_history_pub(c)) return 1;
   for (int i = 1; i <= nwarm; ++i) if (step_advance(c, i)) return 1;
+  if (sync_cg_counter(c)) return 1;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   long l0 = g_launches; long cg0 = c->cg_iters, gm0 = c->gmres_iters, st0 = c->steps;
   cudaEventRecord(e0, c->st);

@@ -230,7 +230,10 @@ static bool cgp_dispatch(const DevMesh& dm, CgArgs& a, cudaStream_t st) {
   }
   if (blocks_per_sm <= 0) return false;
   int want = (int)((dm.E + EPB - 1) / EPB);
-  int grid = std::min(want, nsm * std::min(blocks_per_sm, 2));
+  // small (latency-bound) problems: 2 CTAs/SM keep the grid barrier cheap; HBM-bound sizes need the bandwidth of 8 CTAs/SM
+  static int cap_env = -2; if (cap_env == -2) { const char* e = getenv("NLK_CGP_BLOCKS_PER_SM"); cap_env = e ? atoi(e) : -1; }
+  const int cap = cap_env > 0 ? cap_env : ((size_t)dm.N1 > 1500000 ? 8 : 2);
+  int grid = std::min(want, nsm * std::min(blocks_per_sm, cap));
   if (grid < 1) grid = 1;
   void* args[] = {(void*)&a};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)k_cg_persistent<N, DIM>, dim3(grid), dim3(NT), args, 0, st);
