@@ -75,6 +75,13 @@ __device__ __forceinline__ void contract_t(double* __restrict__ out, const doubl
 __device__ __forceinline__ void load_mat_t(double* s, const double* g, int cnt) {
   for (int i = threadIdx.x; i < cnt; i += blockDim.x) s[i] = g[i];
 }
+// Software L2 prefetch of a future element's operands: blocks are short-lived, so instead of an in-block pipeline every
+// block pulls the lines that the block `dist` elements ahead will need into the 126 MB L2 (DRAM latency -> L2 latency).
+__device__ __forceinline__ void prefetch_l2(const double* base, int ndoubles, int t, int nthreads) {
+  const char* p = reinterpret_cast<const char*>(base);
+  for (int off = t * 128; off < ndoubles * 8; off += nthreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+}
+constexpr int PF_DIST = 296;     // elements ahead (~2 CTAs per SM)
 static inline int tp_threads(int nmax, int d, int np) {
   if (d == 3) { int t = ((nmax * nmax + 31) / 32) * 32; return t > 256 ? 256 : t; }
   int t = ((np + 31) / 32) * 32; return t > 256 ? 256 : (t < 64 ? 64 : t);
@@ -189,13 +196,6 @@ __device__ __forceinline__ void pen_apply(const double (&r)[MI], double (&o)[MO]
   }
 }
 
-// Software L2 prefetch of a future element's operands: blocks are short-lived, so instead of an in-block pipeline every
-// block pulls the lines that the block `dist` elements ahead will need into the 126 MB L2 (DRAM latency -> L2 latency).
-__device__ __forceinline__ void prefetch_l2(const double* base, int ndoubles, int t, int nthreads) {
-  const char* p = reinterpret_cast<const char*>(base);
-  for (int off = t * 128; off < ndoubles * 8; off += nthreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
-}
-constexpr int PF_DIST = 296;      // elements ahead (~2 waves of resident blocks)
 __device__ __forceinline__ void group_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // Component-parallel layout: warp group g (P threads, named barrier g+1) carries velocity component g through all three
@@ -385,6 +385,12 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
   double* sI = sm; double* sIt = sI + m * n; double* sDd = sIt + m * n;
   double* TR = sDd + m * m; double* UF = TR + 3 * npd; double* W1 = UF + npd; double* W2 = W1 + npd; double* ACC = W2 + npd;
   const size_t e = blockIdx.x;
+  if (DIM == 3 && e + PF_DIST < gridDim.x) {
+    const size_t en = e + PF_DIST;
+    prefetch_l2(rxd + en * (size_t)(d * d) * npd, d * d * npd, threadIdx.x, blockDim.x);
+    for (int c = 0; c < d; ++c) prefetch_l2(C.p[c] + en * np1, np1, threadIdx.x, blockDim.x);
+    for (int f = 0; f < nf; ++f) prefetch_l2(u.p[f] + en * np1, np1, threadIdx.x, blockDim.x);
+  }
   load_mat_t(sI, I1dg, m * n); load_mat_t(sIt, I1dtg, m * n); load_mat_t(sDd, Ddg, m * m);
   __syncthreads();
 #pragma unroll 1
@@ -507,6 +513,11 @@ __global__ void k_schwarz_fdm_t(const double* __restrict__ w, double* __restrict
   extern __shared__ double sm[];
   double* sS = sm; double* sSt = sS + d * nn; double* A = sSt + d * nn; double* B = A + np1;
   const size_t e = blockIdx.x;
+  if (DIM == 3 && e + PF_DIST < gridDim.x) {
+    const size_t en = e + PF_DIST;
+    prefetch_l2(w + en * np1, np1, threadIdx.x, blockDim.x); prefetch_l2(dinv + en * np1, np1, threadIdx.x, blockDim.x);
+    prefetch_l2(S + en * (size_t)d * nn, d * nn, threadIdx.x, blockDim.x); prefetch_l2(St + en * (size_t)d * nn, d * nn, threadIdx.x, blockDim.x);
+  }
   load_mat_t(sS, S + e * (size_t)d * nn, d * nn); load_mat_t(sSt, St + e * (size_t)d * nn, d * nn);
   for (int p = threadIdx.x; p < np1; p += blockDim.x) B[p] = w[e * np1 + p];
   __syncthreads();
