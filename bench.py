@@ -117,7 +117,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6, help="time steps in the CPU-baseline sample")
     ap.add_argument("--spinup", type=int, default=30, help="synth3d: untimed time steps before the timed ones (>= warmup)")
     ap.add_argument("--no-cylinder", action="store_true", help="skip the extra cylinder Re=50 matvec block at N=1")
-    ap.add_argument("--coarse-iters", type=int, default=12, help="synth3d: Jacobi-PCG iterations of the sparse coarse solve")
+    ap.add_argument("--coarse-iters", type=int, default=8, help="synth3d: Jacobi-PCG iterations of the sparse coarse solve")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     workload = a.workload or "synth3d"
@@ -298,9 +298,9 @@ def native_arm(workload, steps, warmup, a, rank, world, local):
         # roofline of the dominant kernel at this problem size (CUDA events on the library stream, right after the timed region)
         ms_ax, bytes_ax = ctx.bench_kernel(0, 100)
         roof = {"kernel": "k_axhelm<8,3> (K1, Helmholtz apply inside the Jacobi-PCG)", "bound": "hbm", "achieved": bytes_ax / (ms_ax * 1e-3) / 1e9,
-                "peak": peak, "unit": "GB/s", "frac": bytes_ax / (ms_ax * 1e-3) / 1e9 / peak, "traffic": bytes_ax * (1.168 / 1.177), "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": bytes_ax / (ms_ax * 1e-3) / 1e9 / peak, "traffic": bytes_ax * (1.1698 / 1.1773), "peak_source": peak_src,
                 "us_per_launch": ms_ax * 1e3, "algorithmic_bytes_per_launch": bytes_ax,
-                "traffic_note": "dram read+write / algorithmic = 0.992 from ncu --set full at 31 936 elements (profiles/r01_ncu_full_summary.md), scaled to this size"}
+                "traffic_note": "dram read+write / algorithmic = 0.994 from ncu --set full at 31 936 elements (profiles/r01_ncu_full_summary.md), scaled to this size"}
         other = {}
         for name, which in (("dssum", 1), ("cdabdtp", 2), ("convect", 3), ("precond", 4), ("vec_dot", 5)):
             m_, b_ = ctx.bench_kernel(which, 20)
