@@ -262,6 +262,10 @@ int nlk_ctx_create(const nlk_mesh* m, const nlk_params* p, int32_t device, nlk_c
   NLK_CUDA(cudaSetDevice(device));
   nlk_ctx* c = new nlk_ctx(); c->mesh = m; c->prm = *p; c->device = device;
   NLK_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  if (m->hm.nranks <= 1 && !getenv("NLK_NO_STREAM2")) {
+    NLK_CUDA(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+    NLK_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming)); NLK_CUDA(cudaEventCreateWithFlags(&c->ev_crs, cudaEventDisableTiming));
+  }
   *out = c;
   if (m->hm.nranks > 1) return 0;            // multi-rank: setup is finished by nlk_ctx_comm_init
   if (ctx_setup(c)) return 1;
@@ -287,6 +291,7 @@ int nlk_ctx_destroy(nlk_ctx* c) {
   if (c->h_sc) cudaFreeHost(c->h_sc);
   if (c->h_red) cudaFreeHost(c->h_red);
   if (c->nccl.comm) c->nccl.CommDestroy(c->nccl.comm);
+  if (c->st2) { cudaStreamSynchronize(c->st2); cudaStreamDestroy(c->st2); cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_crs); }
   cudaStreamDestroy(c->st);
   delete c; return 0;
 }

@@ -42,6 +42,8 @@ struct nlk_ctx {
   nlk::DevMesh dm{};
   nlk_params prm{};
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;            // side stream: the coarse-grid branch of the preconditioner runs beside the Schwarz branch
+  cudaEvent_t ev_in = nullptr, ev_crs = nullptr;
   int device = 0;
   nlk::Nccl nccl;
   std::vector<nlk::DevNeighbor> neigh;

@@ -165,13 +165,30 @@ int apply_precond(nlk_ctx* c, const double* r, double* z, const double* in_mul) 
     if (in_mul) launch_lin(z, dm.N2, 1.0, z, 0, nullptr, 0, nullptr, 0, nullptr, in_mul, c->st);
     return 0;
   }
+  // single rank: the coarse branch (restrict -> A0^-1 -> ...) runs on a side stream concurrently with the Schwarz branch
+  const bool side = c->have_coarse && c->st2 && c->nccl.nranks <= 1;
+  if (side) {
+    NLK_CUDA(cudaEventRecord(c->ev_in, c->st));
+    NLK_CUDA(cudaStreamWaitEvent(c->st2, c->ev_in, 0));
+    cudaStream_t main_st = c->st; c->st = c->st2;
+    launch_coarse_restrict(dm, r, in_mul, c->crs_part, c->crs_r, c->st);
+    int rc = 0;
+    if (c->coarse_sparse) rc = coarse_solve_sparse(c, c->crs_r, c->crs_y);
+    else launch_gemv(dm.A0inv, c->crs_r, c->crs_y, (int)dm.nvert, c->st);
+    c->st = main_st;
+    if (rc) return 1;
+    NLK_CUDA(cudaEventRecord(c->ev_crs, c->st2));
+  }
   launch_schwarz_embed(dm, r, in_mul, c->sw_w, c->st);
   if (ctx_gs(c, Ptr3{{c->sw_w, nullptr, nullptr}}, 1)) return 1;
   launch_schwarz_fdm(dm, c->sw_w, c->sw_z, c->sw_t, c->st);
   if (ctx_gs(c, Ptr3{{c->sw_t, nullptr, nullptr}}, 1)) return 1;
   launch_schwarz_gather(dm, c->sw_z, c->sw_t, z, c->st);
   if (c->prm.precond == 3) launch_fill(z, dm.N2, 0.0, c->st);     // debug: coarse term only
-  if (c->have_coarse) {
+  if (side) {
+    NLK_CUDA(cudaStreamWaitEvent(c->st, c->ev_crs, 0));
+    launch_coarse_prolong_add(dm, c->crs_y, z, 1, c->st);
+  } else if (c->have_coarse) {
     launch_coarse_restrict(dm, r, in_mul, c->crs_part, c->crs_r, c->st);
     if (ctx_allreduce(c, c->crs_r, (int)dm.nvert, false)) return 1;
     if (c->coarse_sparse) { if (coarse_solve_sparse(c, c->crs_r, c->crs_y)) return 1; }
