@@ -98,7 +98,7 @@ static int ctx_setup(nlk_ctx* c) {
   if (dev_alloc(c, &c->cg_x, N1) || dev_alloc(c, &c->cg_r, N1) || dev_alloc(c, &c->cg_p, N1) || dev_alloc(c, &c->cg_w, N1)) return 1;
   for (int k = 0; k < 5; ++k) if (dev_alloc(c, &c->pw[k], N2)) return 1;
   // persistent cooperative PCG: single rank and small enough to be launch/latency-bound (NLK_NO_CGP=1 disables it)
-  { size_t lim = 8000000; if (const char* e = getenv("NLK_CGP_MAX_POINTS")) lim = (size_t)atoll(e); c->use_cgp = hm.nranks <= 1 && N1 <= lim && !getenv("NLK_NO_CGP"); }
+  { size_t lim = 1500000; if (const char* e = getenv("NLK_CGP_MAX_POINTS")) lim = (size_t)atoll(e); c->use_cgp = hm.nranks <= 1 && N1 <= lim && !getenv("NLK_NO_CGP"); }
   if (c->use_cgp) {
     for (int k = 0; k < d; ++k) if (dev_alloc(c, &c->cgm_x[k], N1) || dev_alloc(c, &c->cgm_p[k], N1) || dev_alloc(c, &c->cgm_w[k], N1)) return 1;
     if (dev_alloc(c, &c->d_cg_iters, 4) || dev_alloc(c, &c->d_cg_total, 1)) return 1;
