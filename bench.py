@@ -83,10 +83,10 @@ def cylinder_inputs():
 
 def extrude(case, n, layers_total, lz_per_layer=0.5):
     """Extrude the 2-D cylinder mesh (bilinear re-interpolation to lx1=n) into `layers_total` periodic z-layers."""
-    from oracle.sem import gll, interp_matrix      # 1-D nodes only (host-side input generation, not the measured path)
+    from neklab_b200.boxmesh import gll_points, lagrange_interp      # host-side input generation (no oracle on this path)
     c2 = case["coords"]; E2 = c2.shape[0]; n0 = c2.shape[-1]
-    z0, _ = gll(n0); z1, _ = gll(n)
-    I = interp_matrix(z1, z0)
+    z0 = gll_points(n0); z1 = gll_points(n)
+    I = lagrange_interp(z1, z0)
     up = lambda a: np.einsum("qj,pi,e...ji->e...qp", I, I, a)
     xy = up(c2[:, :, 0]); vel = up(case["vel"][:, :, 0])
     L = layers_total

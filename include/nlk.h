@@ -40,8 +40,9 @@ typedef struct {
   const double* ym1;
   const double* zm1;       /* NULL in 2-D */
   const int64_t* vertex;   /* [nelg][2^ndim] .ma2 global vertex ids, lexicographic corners, ALL elements */
-  const char* cbc_v;       /* [nel][2*ndim][3] velocity boundary codes (preprocessor face order)  */
-  const char* cbc_t;       /* [nel][2*ndim][3] temperature codes, or NULL */
+  const char* cbc_v;       /* [nelg][2*ndim][3] velocity boundary codes of ALL elements (preprocessor face order): Dirichlet
+                              flags of shared vertices/edges must be known on every rank that touches them */
+  const char* cbc_t;       /* [nelg][2*ndim][3] temperature codes, or NULL */
   const int32_t* gllnid;   /* [nelg] owning rank of every element (Nek gllnid), or NULL = single rank */
   int32_t rank, nranks;
 } nlk_mesh_desc;

@@ -49,3 +49,34 @@ def box_mesh(nel, lo, hi, periodic=None, bc=None, warp=None):
     # simple partition ids: z-order blocks so that pid // k gives contiguous balanced chunks
     pid = (np.arange(E) * 1024 // E).astype(np.int64)
     return dict(corners=corners, vertex=vertex, cbc=cbc, pid=pid, ndim=d, nel=E)
+
+
+def gll_points(n: int) -> np.ndarray:
+    """n Gauss-Lobatto-Legendre nodes on [-1, 1] (Newton on (1-x^2) P'_{n-1}); host-side input generation only."""
+    N = n - 1
+    x = -np.cos(np.pi * np.arange(n) / N)
+    for _ in range(100):
+        p0 = np.ones_like(x); p1 = x.copy(); d0 = np.zeros_like(x); d1 = np.ones_like(x)
+        for k in range(1, N):
+            p2 = ((2 * k + 1) * x * p1 - k * p0) / (k + 1); d2 = d0 + (2 * k + 1) * p1
+            p0, p1, d0, d1 = p1, p2, d1, d2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dd = (2 * x * d1 - N * (N + 1) * p1) / (1 - x * x)
+        dx = np.zeros_like(x); dx[1:-1] = -d1[1:-1] / dd[1:-1]
+        x = x + dx
+        if np.abs(dx).max() < 1e-16:
+            break
+    x[0], x[-1] = -1.0, 1.0
+    return 0.5 * (x - x[::-1])
+
+
+def lagrange_interp(xto: np.ndarray, xfrom: np.ndarray) -> np.ndarray:
+    """I[i, j] = l_j(xto_i) for the Lagrange basis on xfrom."""
+    out = np.zeros((len(xto), len(xfrom)))
+    for j in range(len(xfrom)):
+        lj = np.ones_like(xto)
+        for k in range(len(xfrom)):
+            if k != j:
+                lj *= (xto - xfrom[k]) / (xfrom[j] - xfrom[k])
+        out[:, j] = lj
+    return out
