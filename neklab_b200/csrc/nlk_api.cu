@@ -297,7 +297,7 @@ int nlk_ctx_destroy(nlk_ctx* c) {
 }
 int nlk_ctx_set_tol(nlk_ctx* c, double vtol, double ptol) { c->prm.vtol = vtol; c->prm.ptol = ptol; return 0; }
 int nlk_ctx_set_dt(nlk_ctx* c, double dt) { if (dt <= 0) { set_error("dt must be positive"); return 1; } c->dt = dt; return 0; }
-int nlk_ctx_sync(nlk_ctx* c) { NLK_CUDA(cudaStreamSynchronize(c->st)); return 0; }
+int nlk_ctx_sync(nlk_ctx* c) { NLK_CUDA(cudaStreamSynchronize(c->st)); NLK_CUDA(cudaGetLastError()); return 0; }
 void* nlk_ctx_stream(nlk_ctx* c) { return (void*)c->st; }
 
 int nlk_ctx_set_forcing(nlk_ctx* c, const double* fx, const double* fy, const double* fz) {

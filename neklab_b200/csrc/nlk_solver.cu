@@ -52,6 +52,7 @@ int ctx_gs(nlk_ctx* c, Ptr3 f, int nf) {
 int ctx_read_scalars(nlk_ctx* c, int count) {
   NLK_CUDA(cudaMemcpyAsync(c->h_red, c->d_red, sizeof(double) * count, cudaMemcpyDeviceToHost, c->st));
   NLK_CUDA(cudaStreamSynchronize(c->st));
+  NLK_CUDA(cudaGetLastError());               // launch-configuration errors are not sticky: surface them here
   return 0;
 }
 
