@@ -36,17 +36,20 @@ __device__ __forceinline__ double mat_at(const double* __restrict__ M, int idx) 
   else return M[idx];
 }
 
-template <int MO, int MI, int DIR, bool ACC, int N0, int N1, int N2, int MAT = MAT_SMEM>
+// PI / PO: x-pitch (row length in doubles) of the input / output tile; 0 = dense.  An odd pitch makes the DIR = 0 stage
+// (consecutive threads one row apart) free of shared-memory bank conflicts.
+template <int MO, int MI, int DIR, bool ACC, int N0, int N1, int N2, int MAT = MAT_SMEM, int PI_ = 0, int PO_ = 0>
 __device__ __forceinline__ void contract_t(double* __restrict__ out, const double* __restrict__ in, const double* __restrict__ M) {
   constexpr int O0 = DIR == 0 ? MO : N0, O1 = DIR == 1 ? MO : N1, O2 = DIR == 2 ? MO : N2;
   constexpr int P0 = DIR == 0 ? 1 : N0, P1 = DIR == 1 ? 1 : N1, P2 = DIR == 2 ? 1 : N2;
   constexpr int NPEN = P0 * P1 * P2;
-  constexpr int istr = DIR == 0 ? 1 : (DIR == 1 ? N0 : N0 * N1);
-  constexpr int ostr = DIR == 0 ? 1 : (DIR == 1 ? O0 : O0 * O1);
+  constexpr int PI = PI_ ? PI_ : N0, PO = PO_ ? PO_ : O0;
+  constexpr int istr = DIR == 0 ? 1 : (DIR == 1 ? PI : PI * N1);
+  constexpr int ostr = DIR == 0 ? 1 : (DIR == 1 ? PO : PO * O1);
   if constexpr (NPEN >= 32) {
     for (int t = threadIdx.x; t < NPEN; t += blockDim.x) {
       const int a = t % P0, b = (t / P0) % P1, c = t / (P0 * P1);
-      const int ibase = a + N0 * (b + N1 * c), obase = a + O0 * (b + O1 * c);
+      const int ibase = a + PI * (b + N1 * c), obase = a + PO * (b + O1 * c);
       double r[MI];
 #pragma unroll
       for (int l = 0; l < MI; ++l) r[l] = in[ibase + l * istr];
@@ -63,11 +66,12 @@ __device__ __forceinline__ void contract_t(double* __restrict__ out, const doubl
     for (int idx = threadIdx.x; idx < TOT; idx += blockDim.x) {
       const int i = idx % O0, j = (idx / O0) % O1, k = idx / (O0 * O1);
       const int r = DIR == 0 ? i : (DIR == 1 ? j : k);
-      const int base = (DIR == 0 ? 0 : i) + N0 * ((DIR == 1 ? 0 : j) + N1 * (DIR == 2 ? 0 : k));
+      const int base = (DIR == 0 ? 0 : i) + PI * ((DIR == 1 ? 0 : j) + N1 * (DIR == 2 ? 0 : k));
+      const int oidx = i + PO * (j + O1 * k);
       double s = 0;
 #pragma unroll
       for (int l = 0; l < MI; ++l) s += M[r * MI + l] * in[base + l * istr];   // (2-D path: per-thread row index -> shared memory)
-      if (ACC) out[idx] += s; else out[idx] = s;
+      if (ACC) out[oidx] += s; else out[oidx] = s;
     }
   }
   __syncthreads();
@@ -383,7 +387,9 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
   constexpr int np1 = n * n * nz, npd = m * m * mz;
   extern __shared__ double sm[];
   double* sI = sm; double* sIt = sI + m * n; double* sDd = sIt + m * n;
-  double* TR = sDd + m * m; double* UF = TR + 3 * npd; double* W1 = UF + npd; double* W2 = W1 + npd; double* ACC = W2 + npd;
+  // 3-D tiles carry odd x-pitches (PN, PM): the x-direction stages then run without shared-memory bank conflicts
+  constexpr int PN = DIM == 3 ? (n | 1) : n, PM = DIM == 3 ? (m | 1) : m, npdP = PM * m * mz;
+  double* TR = sDd + m * m; double* UF = TR + 3 * npdP; double* W1 = UF + npdP; double* W2 = W1 + npdP; double* ACC = W2 + npdP;
   const size_t e = blockIdx.x;
   if (DIM == 3 && e + PF_DIST < gridDim.x) {
     const size_t en = e + PF_DIST;
@@ -396,33 +402,34 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
 #pragma unroll 1
   for (int c = 0; c < d; ++c) {
     const double* cc = C.p[c] + e * np1;
-    for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = cc[i];
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[(i % n) + PN * (i / n)] = cc[i];
     __syncthreads();
     if constexpr (DIM == 2) {
       contract_t<m, n, 0, false, n, n, 1, MAT_I1D>(W2, W1, sI);
       contract_t<m, n, 1, false, m, n, 1, MAT_I1D>(TR + c * npd, W2, sI);
     } else {
-      contract_t<m, n, 0, false, n, n, n, MAT_I1D>(W2, W1, sI);
-      contract_t<m, n, 1, false, m, n, n, MAT_I1D>(W1, W2, sI);
-      contract_t<m, n, 2, false, m, m, n, MAT_I1D>(TR + c * npd, W1, sI);
+      contract_t<m, n, 0, false, n, n, n, MAT_I1D, PN, PM>(W2, W1, sI);
+      contract_t<m, n, 1, false, m, n, n, MAT_I1D, PM, PM>(W1, W2, sI);
+      contract_t<m, n, 2, false, m, m, n, MAT_I1D, PM, PM>(TR + c * npdP, W1, sI);
     }
   }
   const double* rx = rxd + e * (size_t)(d * d) * npd;
   for (int i = threadIdx.x; i < npd; i += blockDim.x) {
-    double cf[3] = {TR[i], TR[npd + i], d == 3 ? TR[2 * npd + i] : 0.0};
+    const int ip = (i % m) + PM * (i / m);
+    double cf[3] = {TR[ip], TR[npdP + ip], d == 3 ? TR[2 * npdP + ip] : 0.0};
 #pragma unroll
     for (int k = 0; k < d; ++k) {
       double s = 0;
 #pragma unroll
       for (int c = 0; c < d; ++c) s += rx[(k * d + c) * npd + i] * cf[c];
-      TR[k * npd + i] = s;
+      TR[k * npdP + ip] = s;
     }
   }
   __syncthreads();
 #pragma unroll 1
   for (int f = 0; f < nf; ++f) {
     const double* uf = u.p[f] + e * np1;
-    for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = uf[i];
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[(i % n) + PN * (i / n)] = uf[i];
     __syncthreads();
     if constexpr (DIM == 2) {
       contract_t<m, n, 0, false, n, n, 1, MAT_I1D>(W2, W1, sI);
@@ -434,24 +441,26 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
       contract_t<n, m, 0, false, m, m, 1, MAT_I1DT>(W1, ACC, sIt);
       contract_t<n, m, 1, false, n, m, 1, MAT_I1DT>(W2, W1, sIt);
     } else {
-      contract_t<m, n, 0, false, n, n, n, MAT_I1D>(W2, W1, sI);
-      contract_t<m, n, 1, false, m, n, n, MAT_I1D>(W1, W2, sI);
-      contract_t<m, n, 2, false, m, m, n, MAT_I1D>(UF, W1, sI);
-      contract_t<m, m, 0, false, m, m, m, MAT_DD>(W1, UF, sDd);
-      for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] = TR[i] * W1[i];
+      // the padded slots of the tiles are never read by a contraction, so the element-wise passes run over the whole
+      // padded range without index arithmetic
+      contract_t<m, n, 0, false, n, n, n, MAT_I1D, PN, PM>(W2, W1, sI);
+      contract_t<m, n, 1, false, m, n, n, MAT_I1D, PM, PM>(W1, W2, sI);
+      contract_t<m, n, 2, false, m, m, n, MAT_I1D, PM, PM>(UF, W1, sI);
+      contract_t<m, m, 0, false, m, m, m, MAT_DD, PM, PM>(W1, UF, sDd);
+      for (int i = threadIdx.x; i < npdP; i += blockDim.x) ACC[i] = TR[i] * W1[i];
       __syncthreads();
-      contract_t<m, m, 1, false, m, m, m, MAT_DD>(W1, UF, sDd);
-      for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] += TR[npd + i] * W1[i];
+      contract_t<m, m, 1, false, m, m, m, MAT_DD, PM, PM>(W1, UF, sDd);
+      for (int i = threadIdx.x; i < npdP; i += blockDim.x) ACC[i] += TR[npdP + i] * W1[i];
       __syncthreads();
-      contract_t<m, m, 2, false, m, m, m, MAT_DD>(W1, UF, sDd);
-      for (int i = threadIdx.x; i < npd; i += blockDim.x) ACC[i] += TR[2 * npd + i] * W1[i];
+      contract_t<m, m, 2, false, m, m, m, MAT_DD, PM, PM>(W1, UF, sDd);
+      for (int i = threadIdx.x; i < npdP; i += blockDim.x) ACC[i] += TR[2 * npdP + i] * W1[i];
       __syncthreads();
-      contract_t<n, m, 0, false, m, m, m, MAT_I1DT>(W1, ACC, sIt);
-      contract_t<n, m, 1, false, n, m, m, MAT_I1DT>(UF, W1, sIt);
-      contract_t<n, m, 2, false, n, n, m, MAT_I1DT>(W2, UF, sIt);
+      contract_t<n, m, 0, false, m, m, m, MAT_I1DT, PM, PN>(W1, ACC, sIt);
+      contract_t<n, m, 1, false, n, m, m, MAT_I1DT, PN, PN>(UF, W1, sIt);
+      contract_t<n, m, 2, false, n, n, m, MAT_I1DT, PN, PN>(W2, UF, sIt);
     }
     double* of = out.p[f] + e * np1;
-    for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[i];
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[(i % n) + PN * (i / n)];
     __syncthreads();
   }
 }
@@ -462,12 +471,18 @@ __global__ void k_convect_adj_t(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __res
                                 const double* __restrict__ I1dtg, const double* __restrict__ Ddg, double alpha, int accumulate) {
   constexpr int n = N, m = MD, d = DIM, nz = DIM == 3 ? N : 1, mz = DIM == 3 ? MD : 1;
   constexpr int np1 = n * n * nz, npd = m * m * mz;
+  constexpr int PN = DIM == 3 ? (n | 1) : n, PM = DIM == 3 ? (m | 1) : m, npdP = PM * m * mz;   // odd x-pitches, see k_convect_t
   extern __shared__ double sm[];
   double* sI = sm; double* sIt = sI + m * n; double* sDd = sIt + m * n;
-  double* AC = sDd + m * m; double* UF = AC + 3 * npd; double* W1 = UF + npd; double* W2 = W1 + npd; double* CF = W2 + npd;
+  double* AC = sDd + m * m; double* UF = AC + 3 * npdP; double* W1 = UF + npdP; double* W2 = W1 + npdP; double* CF = W2 + npdP;
   const size_t e = blockIdx.x;
+  if (DIM == 3 && e + PF_DIST < gridDim.x) {
+    const size_t en = e + PF_DIST;
+    prefetch_l2(rxd + en * (size_t)(d * d) * npd, d * d * npd, threadIdx.x, blockDim.x);
+    for (int c = 0; c < d; ++c) { prefetch_l2(cf.p[c] + en * np1, np1, threadIdx.x, blockDim.x); prefetch_l2(U.p[c] + en * np1, np1, threadIdx.x, blockDim.x); }
+  }
   load_mat_t(sI, I1dg, m * n); load_mat_t(sIt, I1dtg, m * n); load_mat_t(sDd, Ddg, m * m);
-  for (int i = threadIdx.x; i < d * npd; i += blockDim.x) AC[i] = 0.0;
+  for (int i = threadIdx.x; i < d * npdP; i += blockDim.x) AC[i] = 0.0;
   __syncthreads();
   const double* rx = rxd + e * (size_t)(d * d) * npd;
 #pragma unroll 1
@@ -476,20 +491,25 @@ __global__ void k_convect_adj_t(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __res
     for (int pass = 0; pass < 2; ++pass) {
       const double* src = (pass == 0 ? cf.p[j] : U.p[j]) + e * np1;
       double* dst = pass == 0 ? CF : UF;
-      for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = src[i];
+      for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[(i % n) + PN * (i / n)] = src[i];
       __syncthreads();
       if constexpr (DIM == 2) { contract_t<m, n, 0, false, n, n, 1, MAT_I1D>(W2, W1, sI); contract_t<m, n, 1, false, m, n, 1, MAT_I1D>(dst, W2, sI); }
-      else { contract_t<m, n, 0, false, n, n, n, MAT_I1D>(W2, W1, sI); contract_t<m, n, 1, false, m, n, n, MAT_I1D>(W1, W2, sI); contract_t<m, n, 2, false, m, m, n, MAT_I1D>(dst, W1, sI); }
+      else {
+        contract_t<m, n, 0, false, n, n, n, MAT_I1D, PN, PM>(W2, W1, sI);
+        contract_t<m, n, 1, false, m, n, n, MAT_I1D, PM, PM>(W1, W2, sI);
+        contract_t<m, n, 2, false, m, m, n, MAT_I1D, PM, PM>(dst, W1, sI);
+      }
     }
 #pragma unroll
     for (int k = 0; k < d; ++k) {
-      if (k == 0) contract_t<m, m, 0, false, m, m, mz, MAT_DD>(W1, UF, sDd);
-      else if (k == 1) contract_t<m, m, 1, false, m, m, mz, MAT_DD>(W1, UF, sDd);
-      else contract_t<m, m, 2, false, m, m, mz, MAT_DD>(W1, UF, sDd);
+      if (k == 0) contract_t<m, m, 0, false, m, m, mz, MAT_DD, PM, PM>(W1, UF, sDd);
+      else if (k == 1) contract_t<m, m, 1, false, m, m, mz, MAT_DD, PM, PM>(W1, UF, sDd);
+      else contract_t<m, m, 2, false, m, m, mz, MAT_DD, PM, PM>(W1, UF, sDd);
       for (int i = threadIdx.x; i < npd; i += blockDim.x) {
-        double g = CF[i] * W1[i];
+        const int ip = (i % m) + PM * (i / m);
+        double g = CF[ip] * W1[ip];
 #pragma unroll
-        for (int c = 0; c < d; ++c) AC[c * npd + i] += rx[(k * d + c) * npd + i] * g;
+        for (int c = 0; c < d; ++c) AC[c * npdP + ip] += rx[(k * d + c) * npd + i] * g;
       }
       __syncthreads();
     }
@@ -497,9 +517,13 @@ __global__ void k_convect_adj_t(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __res
 #pragma unroll 1
   for (int c = 0; c < d; ++c) {
     if constexpr (DIM == 2) { contract_t<n, m, 0, false, m, m, 1, MAT_I1DT>(W1, AC + c * npd, sIt); contract_t<n, m, 1, false, n, m, 1, MAT_I1DT>(W2, W1, sIt); }
-    else { contract_t<n, m, 0, false, m, m, m, MAT_I1DT>(W1, AC + c * npd, sIt); contract_t<n, m, 1, false, n, m, m, MAT_I1DT>(UF, W1, sIt); contract_t<n, m, 2, false, n, n, m, MAT_I1DT>(W2, UF, sIt); }
+    else {
+      contract_t<n, m, 0, false, m, m, m, MAT_I1DT, PM, PN>(W1, AC + c * npdP, sIt);
+      contract_t<n, m, 1, false, n, m, m, MAT_I1DT, PN, PN>(UF, W1, sIt);
+      contract_t<n, m, 2, false, n, n, m, MAT_I1DT, PN, PN>(W2, UF, sIt);
+    }
     double* of = out.p[c] + e * np1;
-    for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[i];
+    for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[(i % n) + PN * (i / n)];
     __syncthreads();
   }
 }
@@ -510,8 +534,9 @@ template <int N, int DIM>
 __global__ void k_schwarz_fdm_t(const double* __restrict__ w, double* __restrict__ z, double* __restrict__ t, const double* __restrict__ S,
                                 const double* __restrict__ St, const double* __restrict__ dinv) {
   constexpr int n = N, d = DIM, nz = DIM == 3 ? N : 1, np1 = n * n * nz, nn = n * n;
+  constexpr int PN = DIM == 3 ? (n | 1) : n, npP = PN * n * nz;       // odd x-pitch in 3-D (bank-conflict-free x stage)
   extern __shared__ double sm[];
-  double* sS = sm; double* sSt = sS + d * nn; double* A = sSt + d * nn; double* B = A + np1;
+  double* sS = sm; double* sSt = sS + d * nn; double* A = sSt + d * nn; double* B = A + npP;
   const size_t e = blockIdx.x;
   if (DIM == 3 && e + PF_DIST < gridDim.x) {
     const size_t en = e + PF_DIST;
@@ -519,26 +544,26 @@ __global__ void k_schwarz_fdm_t(const double* __restrict__ w, double* __restrict
     prefetch_l2(S + en * (size_t)d * nn, d * nn, threadIdx.x, blockDim.x); prefetch_l2(St + en * (size_t)d * nn, d * nn, threadIdx.x, blockDim.x);
   }
   load_mat_t(sS, S + e * (size_t)d * nn, d * nn); load_mat_t(sSt, St + e * (size_t)d * nn, d * nn);
-  for (int p = threadIdx.x; p < np1; p += blockDim.x) B[p] = w[e * np1 + p];
+  for (int p = threadIdx.x; p < np1; p += blockDim.x) B[(p % n) + PN * (p / n)] = w[e * np1 + p];
   __syncthreads();
   for (int p = threadIdx.x; p < np1; p += blockDim.x) {
     int i = p % n, j = (p / n) % n, k = d == 3 ? p / nn : 1;
     int nb = (i == 0 || i == n - 1) + (j == 0 || j == n - 1) + (d == 3 ? (k == 0 || k == n - 1) : 0);
-    double v = B[p];
-    if (nb == 1) { int ii = clamp_inner_t(i, n), jj = clamp_inner_t(j, n), kk = d == 3 ? clamp_inner_t(k, n) : 0; v -= B[(kk * n + jj) * n + ii]; }
-    A[p] = v;
+    double v = B[i + PN * (p / n)];
+    if (nb == 1) { int ii = clamp_inner_t(i, n), jj = clamp_inner_t(j, n), kk = d == 3 ? clamp_inner_t(k, n) : 0; v -= B[(kk * n + jj) * PN + ii]; }
+    A[i + PN * (p / n)] = v;
   }
   __syncthreads();
   double* res;
-  contract_t<n, n, 0, false, n, n, nz>(B, A, sSt);
-  contract_t<n, n, 1, false, n, n, nz>(A, B, sSt + nn);
+  contract_t<n, n, 0, false, n, n, nz, MAT_SMEM, PN, PN>(B, A, sSt);
+  contract_t<n, n, 1, false, n, n, nz, MAT_SMEM, PN, PN>(A, B, sSt + nn);
   if constexpr (DIM == 3) {
-    contract_t<n, n, 2, false, n, n, nz>(B, A, sSt + 2 * nn);
-    for (int p = threadIdx.x; p < np1; p += blockDim.x) B[p] *= dinv[e * np1 + p];
+    contract_t<n, n, 2, false, n, n, nz, MAT_SMEM, PN, PN>(B, A, sSt + 2 * nn);
+    for (int p = threadIdx.x; p < np1; p += blockDim.x) B[(p % n) + PN * (p / n)] *= dinv[e * np1 + p];
     __syncthreads();
-    contract_t<n, n, 0, false, n, n, nz>(A, B, sS);
-    contract_t<n, n, 1, false, n, n, nz>(B, A, sS + nn);
-    contract_t<n, n, 2, false, n, n, nz>(A, B, sS + 2 * nn);
+    contract_t<n, n, 0, false, n, n, nz, MAT_SMEM, PN, PN>(A, B, sS);
+    contract_t<n, n, 1, false, n, n, nz, MAT_SMEM, PN, PN>(B, A, sS + nn);
+    contract_t<n, n, 2, false, n, n, nz, MAT_SMEM, PN, PN>(A, B, sS + 2 * nn);
     res = A;
   } else {
     for (int p = threadIdx.x; p < np1; p += blockDim.x) A[p] *= dinv[e * np1 + p];
@@ -550,7 +575,7 @@ __global__ void k_schwarz_fdm_t(const double* __restrict__ w, double* __restrict
   for (int p = threadIdx.x; p < np1; p += blockDim.x) {
     int i = p % n, j = (p / n) % n, k = d == 3 ? p / nn : 1;
     int nb = (i == 0 || i == n - 1) + (j == 0 || j == n - 1) + (d == 3 ? (k == 0 || k == n - 1) : 0);
-    double v = res[p];
+    double v = res[i + PN * (p / n)];
     z[e * np1 + p] = v;
     t[e * np1 + p] = nb == 1 ? v : 0.0;
   }
@@ -602,7 +627,8 @@ bool tp_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st) {
   ++g_launches; return true;
 }
 bool tp_schwarz_fdm(const DevMesh& dm, const double* w, double* z, double* t, cudaStream_t st) {
-  size_t smem = (size_t)(2 * dm.ndim * dm.n * dm.n + 2 * dm.np1) * sizeof(double);
+  const size_t npP = dm.ndim == 3 ? (size_t)(dm.n | 1) * dm.n * dm.n : (size_t)dm.np1;
+  size_t smem = (size_t)(2 * dm.ndim * dm.n * dm.n + 2 * npP) * sizeof(double);
   int thr = tp_threads(dm.n, dm.ndim, dm.np1);
 #define FN(N_, D_) { static bool s_ = false; if (!s_) { set_smem(k_schwarz_fdm_t<N_, D_>, smem); s_ = true; } k_schwarz_fdm_t<N_, D_><<<(unsigned)dm.E, thr, smem, st>>>(w, z, t, dm.fdmS, dm.fdmSt, dm.fdmDinv); }
   TP_SWITCH_N(dm.n * 10 + dm.ndim)
@@ -615,8 +641,12 @@ bool tp_schwarz_fdm(const DevMesh& dm, const double* w, double* z, double* t, cu
   case (N_ * 100 + M_) * 10 + 3: FN(N_, M_, 3); break;
 #define TP_SWITCH_NM(key) switch (key) { TP_CASE_NM(4, 6) TP_CASE_NM(5, 8) TP_CASE_NM(6, 9) TP_CASE_NM(7, 11) TP_CASE_NM(8, 12) TP_CASE_NM(9, 14) TP_CASE_NM(10, 15) TP_CASE_NM(12, 18) default: return false; }
 
+static inline size_t convect_smem(const DevMesh& dm) {
+  const size_t npdP = dm.ndim == 3 ? (size_t)(dm.m | 1) * dm.m * dm.m : (size_t)dm.npd;       // padded fine tile
+  return (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * npdP) * sizeof(double);
+}
 bool tp_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double alpha, int accumulate, cudaStream_t st) {
-  size_t smem = (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * dm.npd) * sizeof(double);
+  size_t smem = convect_smem(dm);
   if (smem > 220 * 1024) return false;
   ensure_const_ops(dm, st);
   int thr = tp_threads(dm.m, dm.ndim, dm.npd);
@@ -626,7 +656,7 @@ bool tp_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double al
   ++g_launches; return true;
 }
 bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st) {
-  size_t smem = (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * dm.npd) * sizeof(double);
+  size_t smem = convect_smem(dm);
   if (smem > 220 * 1024) return false;
   ensure_const_ops(dm, st);
   int thr = tp_threads(dm.m, dm.ndim, dm.npd);
