@@ -117,7 +117,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6, help="time steps in the CPU-baseline sample")
     ap.add_argument("--spinup", type=int, default=30, help="synth3d: untimed time steps before the timed ones (>= warmup)")
     ap.add_argument("--no-cylinder", action="store_true", help="skip the extra cylinder Re=50 matvec block at N=1")
-    ap.add_argument("--coarse-iters", type=int, default=12, help="synth3d: Jacobi-PCG iterations of the sparse coarse solve")
+    ap.add_argument("--coarse-iters", type=int, default=8, help="synth3d: Jacobi-PCG iterations of the sparse coarse solve")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     workload = a.workload or "synth3d"

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from neklab_b200 import api, build  # noqa: E402
 
-NAMES = {0: "axhelm (K1)", 1: "dssum (K2)", 2: "cdabdtp = opgradt+gs+opdiv (K6)", 3: "convect x d fields (K3)", 4: "precond Schwarz (K10)", 5: "vec dot (K12)"}
+NAMES = {0: "axhelm (K1)", 1: "dssum (K2)", 2: "cdabdtp = opgradt+gs+opdiv (K6)", 3: "convect x d fields (K3)", 4: "precond Schwarz (K10)", 5: "vec dot (K12)", 6: "coarse solve, sparse PCG (K11)", 7: "Schwarz branch alone (K10)"}
 
 
 def main():
@@ -21,13 +21,14 @@ def main():
     ap.add_argument("--which", default="0,1,2,3,4,5")
     ap.add_argument("--nrep", type=int, default=20)
     ap.add_argument("--lx1", type=int, default=8)
+    ap.add_argument("--precond", type=int, default=2, help="2 Schwarz only (default), 4 Schwarz + sparse coarse (needed for --which 6)")
     a = ap.parse_args()
     build.build()
     peak, src = bench.load_peaks()
     case = bench.cylinder_inputs()
     coords, U, vertex, cbc = bench.extrude(case, a.lx1, a.layers)
     mesh = api.Mesh(coords, vertex, cbc, a.lx1 * 3 // 2)
-    ctx = api.Context(mesh, api.default_params(viscosity=0.02, precond=2))
+    ctx = api.Context(mesh, api.default_params(viscosity=0.02, precond=a.precond))
     npts = coords.shape[0] * a.lx1 ** 3
     out = {"elements": int(coords.shape[0]), "points": int(npts), "peak_GBps": peak, "peak_source": src, "kernels": {}}
     for w in [int(x) for x in a.which.split(",")]:

@@ -207,7 +207,7 @@ int nlk_test_pressure(nlk_ctx* c, const double* rhs, double tol, double* x, int3
 int nlk_test_precond(nlk_ctx* c, const double* r, double* z);                                /* K10/K11 */
 int nlk_test_cfl(nlk_ctx* c, const double* ux, const double* uy, const double* uz, double dt, double* cfl); /* K14 */
 /* time a device-resident kernel nrep times on the ctx stream with CUDA events; returns mean ms per launch.
- * which: 0 axhelm, 1 dssum, 2 cdabdtp, 3 convect(all comps), 4 precond, 5 vec dot, 6 cg iteration */
+ * which: 0 axhelm, 1 dssum, 2 cdabdtp, 3 convect(all comps), 4 precond, 5 vec dot, 6 sparse coarse solve, 7 Schwarz branch of the preconditioner */
 int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_launch, double* algo_bytes);
 
 #ifdef __cplusplus

@@ -96,6 +96,7 @@ static int ctx_setup(nlk_ctx* c) {
   if (c->prm.ifheat) { if (dev_alloc(c, &c->tlag[0], N1) || dev_alloc(c, &c->tlag[1], N1) || dev_alloc(c, &c->vgradt1, N1) || dev_alloc(c, &c->vgradt2, N1) || dev_alloc(c, &c->bq, N1)) return 1; }
   for (int k = 0; k < 8; ++k) if (dev_alloc(c, &c->wk[k], N1)) return 1;
   if (dev_alloc(c, &c->cg_x, N1) || dev_alloc(c, &c->cg_r, N1) || dev_alloc(c, &c->cg_p, N1) || dev_alloc(c, &c->cg_w, N1)) return 1;
+  if (dev_alloc(c, &c->cg_pap_partial, (size_t)hm.E + 1) || dev_alloc(c, &c->cg_pap_counter, 4)) return 1;
   for (int k = 0; k < 5; ++k) if (dev_alloc(c, &c->pw[k], N2)) return 1;
   // persistent cooperative PCG: single rank and small enough to be launch/latency-bound (NLK_NO_CGP=1 disables it)
   { size_t lim = 1500000; if (const char* e = getenv("NLK_CGP_MAX_POINTS")) lim = (size_t)atoll(e); c->use_cgp = hm.nranks <= 1 && N1 <= lim && !getenv("NLK_NO_CGP"); }
@@ -243,7 +244,7 @@ int nlk_params_default(nlk_params* p) {
   std::memset(p, 0, sizeof(*p));
   p->viscosity = 1.0; p->density = 1.0; p->torder = 3; p->vtol = 1e-9; p->ptol = 1e-7; p->ifheat = 0; p->conductivity = 1.0; p->rhocp = 1.0;
   p->ttol = 1e-9; p->filter_weight = 0.0; p->filter_cutoff = 1.0; p->cg_maxit = 1000; p->gmres_maxit = 100; p->lgmres = 30; p->precond = 1;
-  p->pr_proj = 0; p->cfl_limit = 0.5; p->rst_mode = 0; p->coarse_iters = 12;
+  p->pr_proj = 0; p->cfl_limit = 0.5; p->rst_mode = 0; p->coarse_iters = 8;
   return 0;
 }
 
@@ -262,8 +263,13 @@ int nlk_ctx_create(const nlk_mesh* m, const nlk_params* p, int32_t device, nlk_c
   NLK_CUDA(cudaSetDevice(device));
   nlk_ctx* c = new nlk_ctx(); c->mesh = m; c->prm = *p; c->device = device;
   NLK_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  c->ph.on = getenv("NLK_PHASES") != nullptr;
   if (m->hm.nranks <= 1 && !getenv("NLK_NO_STREAM2")) {
-    NLK_CUDA(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+    // highest priority: the coarse branch is a chain of tiny kernels whose blocks must slip in between the waves of the
+    // Schwarz kernels on the main stream instead of queueing behind each of them
+    int prio_lo = 0, prio_hi = 0;
+    NLK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    NLK_CUDA(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, prio_hi));
     NLK_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming)); NLK_CUDA(cudaEventCreateWithFlags(&c->ev_crs, cudaEventDisableTiming));
   }
   *out = c;
@@ -287,6 +293,15 @@ int nlk_ctx_comm_init(nlk_ctx* c, const char id[128], int32_t rank, int32_t nran
 int nlk_ctx_destroy(nlk_ctx* c) {
   if (!c) return 0;
   cudaStreamSynchronize(c->st);
+  if (c->ph.on && c->ph.steps > 0) {
+    static const char* names[nlk::PH_COUNT] = {"makef (convection, ext/bdf)", "velocity residual", "Helmholtz PCG", "pressure rhs", "pressure solve (total)",
+                                               "  preconditioner", "  E apply", "  orthogonalisation + host", "velocity correction", "heat", "filter"};
+    fprintf(stderr, "[nlk phases] %ld steps, rank %d\n", c->ph.steps, c->nccl.rank);
+    for (int i = 0; i < nlk::PH_COUNT; ++i)
+      if (c->ph.calls[i]) fprintf(stderr, "[nlk phases] %-32s %9.3f ms/step  (%6.1f calls/step)\n", names[i], c->ph.ms[i] / c->ph.steps, (double)c->ph.calls[i] / c->ph.steps);
+    for (cudaEvent_t e : c->ph.pool) cudaEventDestroy(e);
+  }
+  if (c->crs_graph) cudaGraphExecDestroy(c->crs_graph);
   for (void* p : c->allocs) cudaFree(p);
   if (c->h_sc) cudaFreeHost(c->h_sc);
   if (c->h_red) cudaFreeHost(c->h_red);
@@ -738,6 +753,11 @@ int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_lau
       case 3: launch_convect(dm, CPtr4{{c->wk[3], c->wk[4], c->wk[5], nullptr}}, d, CPtr3{{c->wk[0], c->wk[1], c->wk[2]}}, Ptr4{{c->bf[0], c->bf[1], c->bf[2], nullptr}}, 1.0, 0, c->st); break;
       case 4: return apply_precond(c, c->pw[3], c->pw[4], nullptr);
       case 5: { CPtr4 A{{c->wk[0], c->wk[1], c->wk[2], nullptr}}; launch_dot(dm.N1, A, A, d, dm.bm1, c->d_red, c->red, c->st); break; }
+      case 6: if (!c->coarse_sparse) { set_error("bench 6: the context has no sparse coarse level"); return 1; } return coarse_solve_sparse(c, c->crs_r, c->crs_y);
+      case 7: if (!c->have_schwarz) { set_error("bench 7: no Schwarz level"); return 1; }      // Schwarz branch alone
+              launch_schwarz_embed(dm, c->pw[3], nullptr, c->sw_w, c->st); if (ctx_gs(c, Ptr3{{c->sw_w, nullptr, nullptr}}, 1)) return 1;
+              launch_schwarz_fdm(dm, c->sw_w, c->sw_z, c->sw_t, c->st); if (ctx_gs(c, Ptr3{{c->sw_t, nullptr, nullptr}}, 1)) return 1;
+              launch_schwarz_gather(dm, c->sw_z, c->sw_t, c->pw[4], c->st); break;
       default: set_error("unknown bench kernel"); return 1;
     }
     return 0;
@@ -758,6 +778,8 @@ int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_lau
     case 3: bytes = (3.0 * d + d * d) * 8.0 * N1; break;
     case 4: bytes = 2 * 8.0 * N2 + 6 * 8.0 * N1; break;
     case 5: bytes = (d + 1) * 8.0 * N1; break;
+    case 6: bytes = (double)c->crs_iters * (12.0 * (double)c->crs_nnz + 9 * 8.0 * (double)dm.nvert); break;   // CSR values + indices per SpMV, vectors
+    case 7: bytes = 2 * 8.0 * N2 + 6 * 8.0 * N1; break;
   }
   if (algo_bytes) *algo_bytes = bytes;
   return 0;

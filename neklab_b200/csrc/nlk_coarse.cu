@@ -20,84 +20,119 @@ __device__ __forceinline__ double warp_sum_c(double v) {
   return v;
 }
 
-// scal layout: [0] rz, [1] pq, [2] alpha, [3] beta, [4] rz_new, [5] done
-// q = A p (warp per row) and pq = p.q ; the last block finalises alpha = rz / pq
-__global__ void __launch_bounds__(256)
-k_crs_spmv_dot(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ p,
-               double* __restrict__ q, int n, double* scal, double* partial, unsigned int* counter) {
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  double acc = 0.0;
-  for (int row = blockIdx.x * wpb + wib; row < n; row += gridDim.x * wpb) {
-    double s = 0.0;
-    for (int k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) s += val[k] * p[col[k]];
-    s = warp_sum_c(s);
-    if (lane == 0) { q[row] = s; acc += s * p[row]; }
+// Reductions without atomics or "last block" tails: a kernel leaves one partial sum per block, and every WARP of the next
+// kernel re-sums those partials itself in a fixed order (bit-identical alpha / beta everywhere, deterministic, and no
+// block barrier: the partial loads are issued first and overlap the kernel's own gather chain -- these kernels are pure
+// latency chains of a few microseconds).  rz partials are double-buffered by iteration parity (beta needs the current
+// and the previous r.z).
+constexpr int CRS_MAXB_RZ = 296, CRS_MAXB_PQ = 1184;       // blocks per kernel = partials per buffer
+template <int MAXB>
+struct CrsPartials {                                        // the calling lane's share of the partials, kept in registers
+  double v[(MAXB + 31) / 32];
+  __device__ __forceinline__ void load(const double* __restrict__ partial, int nb, int lane) {
+#pragma unroll
+    for (int k = 0; k < (MAXB + 31) / 32; ++k) { const int b = lane + 32 * k; v[k] = b < nb ? partial[b] : 0.0; }
   }
-  __shared__ double sp[8]; __shared__ int last;
+  __device__ __forceinline__ double total() const {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < (MAXB + 31) / 32; ++k) t += v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+  }
+};
+__device__ __forceinline__ void crs_block_partial(double acc, double* __restrict__ partial) {
+  __shared__ double sp[8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  acc = warp_sum_c(acc);
   if (lane == 0) sp[wib] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0; for (int i = 0; i < wpb; ++i) t += sp[i];
-    partial[blockIdx.x] = t; __threadfence();
-    last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (last && threadIdx.x < 32) {
-    __threadfence();
-    double t = 0; for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&partial[b]);
-    t = warp_sum_c(t);
-    if (lane == 0) { scal[1] = t; scal[2] = (t != 0.0) ? scal[0] / t : 0.0; *counter = 0u; }
-  }
+  if (threadIdx.x == 0) { double t = 0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sp[i]; partial[blockIdx.x] = t; }
 }
 
-// x += alpha p ; r -= alpha q ; z = dinv r ; rz_new = r.z ; last block: beta = rz_new / rz, rz = rz_new
+// Search-direction update folded into the SpMV (one kernel less per iteration): with s = A z,
+//   p <- z + beta p ,  q = A p <- s + beta q ,  pq partial = p.q       (beta = rz / rz_prev, 0 in the first iteration)
+// Every row's p and q are touched by its own warp only; the gather reads z, which this kernel does not write.
 __global__ void __launch_bounds__(256)
-k_crs_update(double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, const double* __restrict__ p, const double* __restrict__ q,
-             const double* __restrict__ dinv, int n, double* scal, double* partial, unsigned int* counter, int first) {
-  const double alpha = first ? 0.0 : scal[2];
+k_crs_spmv_pq(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ z,
+              double* __restrict__ p, double* __restrict__ q, int n, const double* __restrict__ rz_cur, const double* __restrict__ rz_prev,
+              int nb_rz, int first, double* __restrict__ pq_partial) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  CrsPartials<CRS_MAXB_RZ> pa, pb;
+  if (!first) { pa.load(rz_cur, nb_rz, lane); pb.load(rz_prev, nb_rz, lane); }
+  double acc = 0.0, beta = 0.0; bool have_beta = first;
+  for (int row = blockIdx.x * wpb + wib; row < n; row += gridDim.x * wpb) {
+    double s = 0.0;
+    for (int k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) s += val[k] * z[col[k]];
+    s = warp_sum_c(s);
+    if (!have_beta) { const double a = pa.total(), b = pb.total(); beta = b != 0.0 ? a / b : 0.0; have_beta = true; }
+    if (lane == 0) {
+      const double pn = z[row] + beta * p[row], qn = s + beta * q[row];
+      p[row] = pn; q[row] = qn; acc += pn * qn;
+    }
+  }
+  crs_block_partial(lane == 0 ? acc : 0.0, pq_partial);
+}
+
+// first: x = 0, p = q = 0, r = rhs ; else x += alpha p, r -= alpha q (alpha = rz / pq) ; then z = dinv r and the r.z partial
+__global__ void __launch_bounds__(256)
+k_crs_update(double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ q,
+             const double* __restrict__ dinv, const double* __restrict__ rhs, int n, const double* __restrict__ rz_cur, int nb_rz,
+             const double* __restrict__ pq_partial, int nb_pq, int first, double* __restrict__ rz_out) {
+  const int lane = threadIdx.x & 31;
+  double alpha = 0.0;
+  if (!first) {
+    CrsPartials<CRS_MAXB_RZ> pa; CrsPartials<CRS_MAXB_PQ> pb;
+    pa.load(rz_cur, nb_rz, lane); pb.load(pq_partial, nb_pq, lane);
+    const double a = pa.total(), b = pb.total();
+    alpha = b != 0.0 ? a / b : 0.0;
+  }
   double acc = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    double ri = r[i];
-    if (!first) { x[i] += alpha * p[i]; ri -= alpha * q[i]; r[i] = ri; }
-    double zi = ri * dinv[i]; z[i] = zi; acc += ri * zi;
+    double ri;
+    if (first) { ri = rhs[i]; x[i] = 0.0; p[i] = 0.0; q[i] = 0.0; }
+    else { x[i] += alpha * p[i]; ri = r[i] - alpha * q[i]; }
+    r[i] = ri;
+    const double zi = ri * dinv[i]; z[i] = zi; acc += ri * zi;
   }
-  acc = warp_sum_c(acc);
-  __shared__ double sp[8]; __shared__ int last;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  if (lane == 0) sp[wib] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0; for (int i = 0; i < wpb; ++i) t += sp[i];
-    partial[blockIdx.x] = t; __threadfence();
-    last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (last && threadIdx.x < 32) {
-    __threadfence();
-    double t = 0; for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&partial[b]);
-    t = warp_sum_c(t);
-    if (lane == 0) { scal[3] = (first || scal[0] == 0.0) ? 0.0 : t / scal[0]; scal[0] = t; *counter = 0u; }
-  }
+  crs_block_partial(acc, rz_out);
 }
-__global__ void k_crs_p(double* __restrict__ p, const double* __restrict__ z, int n, const double* scal) {
-  const double beta = scal[3];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = z[i] + beta * p[i];
+
+// The solve is a fixed sequence of 1 + 2*iters tiny kernels (a few microseconds each); issued one by one it is bound by
+// launch latency (phase timing, 7 984 elements: the coarse branch made the preconditioner 0.5 ms per application against
+// 0.16 ms for the Schwarz branch).  The sequence is therefore captured once into a CUDA graph and replayed.
+static int coarse_issue(nlk_ctx* c, const double* rc, double* yc, cudaStream_t st) {
+  const int n = (int)c->dm.nvert;
+  const int gu = std::min((n + 255) / 256, CRS_MAXB_RZ), gs = std::min((n + 7) / 8, CRS_MAXB_PQ);     // SpMV: one row per warp while it lasts
+  double* rzb[2] = {c->crs_partial, c->crs_partial + CRS_MAXB_RZ}; double* pqb = c->crs_partial + 2 * CRS_MAXB_RZ;
+  k_crs_update<<<gu, 256, 0, st>>>(yc, c->crs_rr, c->crs_z, c->crs_p, c->crs_q, c->crs_dinv, rc, n, nullptr, 0, nullptr, 0, 1, rzb[0]);
+  for (int it = 0; it < c->crs_iters; ++it) {
+    const double* cur = rzb[it & 1]; double* nxt = rzb[(it + 1) & 1];
+    k_crs_spmv_pq<<<gs, 256, 0, st>>>(c->crs_rowptr, c->crs_col, c->crs_val, c->crs_z, c->crs_p, c->crs_q, n, cur, nxt, gu, it == 0, pqb);
+    k_crs_update<<<gu, 256, 0, st>>>(yc, c->crs_rr, c->crs_z, c->crs_p, c->crs_q, c->crs_dinv, rc, n, cur, gu, pqb, gs, 0, nxt);
+  }
+  NLK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int coarse_solve_sparse(nlk_ctx* c, const double* rc, double* yc) {
-  const int n = (int)c->dm.nvert;
   cudaStream_t st = c->st;
-  const int gu = std::min((n + 255) / 256, 296), gs = std::min((n + 7) / 8, 1184);
-  NLK_CUDA(cudaMemsetAsync(yc, 0, sizeof(double) * n, st));
-  NLK_CUDA(cudaMemsetAsync(c->crs_p, 0, sizeof(double) * n, st));
-  NLK_CUDA(cudaMemcpyAsync(c->crs_rr, rc, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-  double* partial = c->red.partial; unsigned int* counter = c->red.counter;
-  k_crs_update<<<gu, 256, 0, st>>>(yc, c->crs_rr, c->crs_z, c->crs_p, c->crs_q, c->crs_dinv, n, c->crs_scal, partial, counter, 1); ++g_launches;
-  for (int it = 0; it < c->crs_iters; ++it) {
-    k_crs_p<<<gu, 256, 0, st>>>(c->crs_p, c->crs_z, n, c->crs_scal); ++g_launches;
-    k_crs_spmv_dot<<<gs, 256, 0, st>>>(c->crs_rowptr, c->crs_col, c->crs_val, c->crs_p, c->crs_q, n, c->crs_scal, partial, counter); ++g_launches;
-    k_crs_update<<<gu, 256, 0, st>>>(yc, c->crs_rr, c->crs_z, c->crs_p, c->crs_q, c->crs_dinv, n, c->crs_scal, partial, counter, 0); ++g_launches;
+  static const bool no_graph = getenv("NLK_NO_GRAPH") != nullptr;
+  if (no_graph) { g_launches += 1 + 2 * c->crs_iters; return coarse_issue(c, rc, yc, st); }
+  if (!c->crs_graph || c->crs_graph_in != rc || c->crs_graph_out != yc) {
+    if (c->crs_graph) { cudaGraphExecDestroy(c->crs_graph); c->crs_graph = nullptr; }
+    cudaGraph_t g = nullptr;
+    NLK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    int rc_issue = coarse_issue(c, rc, yc, st);
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc_issue || e != cudaSuccess) { if (g) cudaGraphDestroy(g); set_error("coarse solve: graph capture failed"); return 1; }
+    NLK_CUDA(cudaGraphInstantiate(&c->crs_graph, g, 0));
+    cudaGraphDestroy(g);
+    c->crs_graph_in = rc; c->crs_graph_out = yc;
   }
+  NLK_CUDA(cudaGraphLaunch(c->crs_graph, st));
+  g_launches += 1 + 2 * c->crs_iters;           // kernels executed by the graph
   return 0;
 }
 
@@ -151,7 +186,8 @@ int coarse_setup_sparse(nlk_ctx* c) {
   std::vector<double> dinv(nvt, 1.0);
   for (int64_t w = 0; w < nvt; ++w) for (int32_t k = rowptr[w]; k < rowptr[w + 1]; ++k) if (col[k] == w) dinv[w] = val[k] != 0.0 ? 1.0 / val[k] : 1.0;
   if (dev_upload(c, &c->crs_rowptr, rowptr) || dev_upload(c, &c->crs_col, col) || dev_upload(c, &c->crs_val, val) || dev_upload(c, &c->crs_dinv, dinv)) return 1;
-  if (dev_alloc(c, &c->crs_p, nvt) || dev_alloc(c, &c->crs_q, nvt) || dev_alloc(c, &c->crs_z, nvt) || dev_alloc(c, &c->crs_rr, nvt) || dev_alloc(c, &c->crs_scal, 8)) return 1;
+  if (dev_alloc(c, &c->crs_p, nvt) || dev_alloc(c, &c->crs_q, nvt) || dev_alloc(c, &c->crs_z, nvt) || dev_alloc(c, &c->crs_rr, nvt)) return 1;
+  if (dev_alloc(c, &c->crs_partial, 2 * CRS_MAXB_RZ + CRS_MAXB_PQ)) return 1;
   c->crs_nnz = nnz; c->coarse_sparse = true; c->have_coarse = true;
   if (c->crs_iters <= 0) c->crs_iters = 12;
   if (getenv("NLK_VERBOSE")) printf("[nlk] sparse coarse operator: %lld vertices, %lld nnz, %d colours, %d PCG iterations per apply\n", (long long)nvt, (long long)nnz, ncolors, c->crs_iters);

@@ -37,7 +37,34 @@ struct DevNeighbor {
 
 }  // namespace nlk
 
+// Phase timing of the time step (diagnostics; enabled by the environment variable NLK_PHASES=1, printed to stderr when the
+// context is destroyed): CUDA-event pairs recorded on the library stream around each phase and resolved once per step.
+namespace nlk {
+enum Phase { PH_MAKEF, PH_VRES, PH_HELM, PH_PRHS, PH_PRES, PH_PRECOND, PH_EAPPLY, PH_ORTH, PH_CORR, PH_HEAT, PH_FILTER, PH_COUNT };
+struct PhaseTimer {
+  bool on = false;
+  struct Rec { int id; cudaEvent_t a, b; };
+  std::vector<Rec> recs; std::vector<cudaEvent_t> pool;
+  double ms[PH_COUNT] = {0}; long calls[PH_COUNT] = {0}; long steps = 0;
+  cudaEvent_t get() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
+  int begin(int id, cudaStream_t st) { if (!on) return -1; Rec r{id, get(), get()}; cudaEventRecord(r.a, st); recs.push_back(r); return (int)recs.size() - 1; }
+  void end(int idx, cudaStream_t st) { if (idx >= 0) cudaEventRecord(recs[idx].b, st); }
+  void resolve(cudaStream_t st) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    for (auto& r : recs) { float t = 0; cudaEventElapsedTime(&t, r.a, r.b); ms[r.id] += t; ++calls[r.id]; pool.push_back(r.a); pool.push_back(r.b); }
+    recs.clear(); ++steps;
+  }
+};
+struct PhaseScope {
+  PhaseTimer& t; cudaStream_t st; int idx;
+  PhaseScope(PhaseTimer& t_, int id, cudaStream_t st_) : t(t_), st(st_), idx(t_.begin(id, st_)) {}
+  ~PhaseScope() { t.end(idx, st); }
+};
+}  // namespace nlk
+
 struct nlk_ctx {
+  nlk::PhaseTimer ph;
   const nlk_mesh* mesh = nullptr;
   nlk::DevMesh dm{};
   nlk_params prm{};
@@ -86,7 +113,10 @@ struct nlk_ctx {
   // sparse coarse operator (large vertex counts): CSR of R0 E R0^T + Jacobi-PCG work vectors, all device-resident
   bool coarse_sparse = false; int crs_iters = 0; int64_t crs_nnz = 0;
   int32_t* crs_rowptr = nullptr; int32_t* crs_col = nullptr; double* crs_val = nullptr; double* crs_dinv = nullptr;
-  double* crs_p = nullptr, *crs_q = nullptr, *crs_z = nullptr, *crs_rr = nullptr, *crs_scal = nullptr;
+  double* crs_p = nullptr, *crs_q = nullptr, *crs_z = nullptr, *crs_rr = nullptr;
+  double* cg_pap_partial = nullptr; unsigned int* cg_pap_counter = nullptr;   // block partials of p.Ap reduced inside the Helmholtz kernel
+  double* crs_partial = nullptr;         // per-block partial sums of the coarse PCG (own scratch: the solve runs on the side stream)
+  cudaGraphExec_t crs_graph = nullptr; const double* crs_graph_in = nullptr; double* crs_graph_out = nullptr;   // the fixed-count PCG as one graph launch
   // pressure projection (residualProj)
   double* proj_X = nullptr, *proj_EX = nullptr, *proj_w = nullptr, *proj_xbar = nullptr; int nproj = 0;
   // time stepping

@@ -92,7 +92,9 @@ bool launch_cg_persistent(const DevMesh& dm, CgArgs& a, cudaStream_t st);
 // K1  axhelm (hmholtz.f): w = h1*(D^T G D)u + h2*B u, element-local.  If pz != nullptr the CG direction update
 //     p = r*dinv + beta*p is fused in front (u is then p, read-modify-write), with dinv = 1/(h1*diagA+h2*diagB).
 void launch_axhelm(const DevMesh& dm, const double* u, double* w, double h1, double h2, cudaStream_t st);
-void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, double h1, double h2, const SolverScal* sc, cudaStream_t st);
+// pap_partial: one double per launched block (>= number of elements); with defer != 0 only sc->red[2] is stored (multi-rank)
+void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, double h1, double h2, SolverScal* sc,
+                      double* pap_partial, unsigned int* pap_counter, int defer, cudaStream_t st);
 // K2  dssum (gs_op add) on up to 3 fields; local part.
 void launch_gs(const DevMesh& dm, Ptr3 f, int nf, cudaStream_t st);
 // generic pointwise: out = (a0*x0 + a1*x1 + a2*x2 + a3*x3) * (mul ? mul : 1)

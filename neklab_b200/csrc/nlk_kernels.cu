@@ -92,14 +92,18 @@ static void ensure_const_D(const DevMesh& dm, cudaStream_t st) {
   cudaMemcpyToSymbolAsync(c_D, dm.D, sizeof(double) * dm.n * dm.n, 0, cudaMemcpyDeviceToDevice, st);
   c_D_n = dm.n;
 }
+__device__ __forceinline__ void cg_finalize_pap(SolverScal* sc);
 // One element per (threadIdx.y) slice; thread (i,j) owns the k-column of the element (register-tiled k-loop, 3-D).
-// FUSE_CG: the CG search-direction update p = r/(h1*diagA+h2*diagB) + beta*p is applied while loading.
+// FUSE_CG: the CG search-direction update p = r/(h1*diagA+h2*diagB) + beta*p is applied while loading, and p.Ap is reduced
+// on the way out: p is continuous and masked, so the sum over local copies of p * w(unassembled) equals the assembled,
+// multiplicity-weighted inner product Nek's cggo takes after dssum -- one full pass over w, p, mask and mult saved per
+// iteration.  Block partials -> last block sums them in a fixed order (deterministic).
 template <int N, int DIM, bool FUSE_CG>
 __global__ void __launch_bounds__(N * N * (N * N >= 100 ? 1 : (N * N >= 64 ? 2 : 4)), (N == 8 ? 8 : 1))
 k_axhelm(const double* __restrict__ u, double* __restrict__ pio, const double* __restrict__ r, double* __restrict__ w,
          const double* __restrict__ G, const double* __restrict__ bm1, const double* __restrict__ Dg,
          const double* __restrict__ diagA, const double* __restrict__ diagB, double h1, double h2,
-         const SolverScal* __restrict__ sc, int64_t E) {
+         SolverScal* __restrict__ sc, int64_t E, double* __restrict__ pap_partial, unsigned int* pap_counter, int defer) {
   constexpr int NZ = DIM == 3 ? N : 1;
   constexpr int NN = N * N;
   constexpr int NP = NN * NZ;
@@ -179,20 +183,48 @@ k_axhelm(const double* __restrict__ u, double* __restrict__ pio, const double* _
     }
     __syncthreads();
   }
+  double pap = 0.0;
   if (active) {
 #pragma unroll
-    for (int k = 0; k < NZ; ++k) { size_t g = eb + k * NN + tid; w[g] = h1 * rw[k] + h2 * bm1[g] * ru[k]; }
+    for (int k = 0; k < NZ; ++k) { size_t g = eb + k * NN + tid; double wv = h1 * rw[k] + h2 * bm1[g] * ru[k]; w[g] = wv; if (FUSE_CG) pap += ru[k] * wv; }
+  }
+  if (FUSE_CG) {
+    constexpr int NT = NN * EPB;
+    double* sred = &s_gr[0][0];                     // free after the last barrier of the k-loop
+    __shared__ int s_last;
+    const int lt = le * NN + tid;
+    sred[lt] = pap;
+    __syncthreads();
+    if (lt < 32) { double t = 0; for (int q = lt; q < NT; q += 32) t += sred[q]; sred[lt] = t; }
+    __syncthreads();
+    if (lt == 0) {
+      double t = 0; for (int q = 0; q < (NT < 32 ? NT : 32); ++q) t += sred[q];
+      pap_partial[blockIdx.x] = t; __threadfence();
+      s_last = (atomicAdd(pap_counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      double t = 0; for (unsigned b = lt; b < gridDim.x; b += NT) t += __ldcg(&pap_partial[b]);
+      sred[lt] = t;
+      __syncthreads();
+      if (lt == 0) {
+        double tt = 0; for (int q = 0; q < NT; ++q) tt += sred[q];
+        sc->red[2] = tt; if (!defer) cg_finalize_pap(sc);
+        *pap_counter = 0u;
+      }
+    }
   }
 }
 
 template <int N, int DIM>
 static void axhelm_dispatch(const DevMesh& dm, const double* u, double* pio, const double* r, double* w, double h1, double h2,
-                            const SolverScal* sc, bool fuse, cudaStream_t st) {
+                            SolverScal* sc, bool fuse, double* pap_partial, unsigned int* pap_counter, int defer, cudaStream_t st) {
   constexpr int EPB = N * N >= 100 ? 1 : (N * N >= 64 ? 2 : 4);
   ensure_const_D(dm, st);
   dim3 block(N * N, EPB), grid(cdiv(dm.E, EPB));
-  if (fuse) k_axhelm<N, DIM, true><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, dm.diagA, dm.diagB, h1, h2, sc, dm.E);
-  else k_axhelm<N, DIM, false><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, dm.diagA, dm.diagB, h1, h2, sc, dm.E);
+  if (fuse) k_axhelm<N, DIM, true><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, dm.diagA, dm.diagB, h1, h2, sc, dm.E, pap_partial, pap_counter, defer);
+  else k_axhelm<N, DIM, false><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, dm.diagA, dm.diagB, h1, h2, nullptr, dm.E, nullptr, nullptr, 0);
   LAUNCH_COUNT();
 }
 
@@ -211,10 +243,11 @@ static void axhelm_dispatch(const DevMesh& dm, const double* u, double* pio, con
   }
 
 void launch_axhelm(const DevMesh& dm, const double* u, double* w, double h1, double h2, cudaStream_t st) {
-  NLK_FOR_N(axhelm_dispatch, dm, u, nullptr, nullptr, w, h1, h2, nullptr, false, st)
+  NLK_FOR_N(axhelm_dispatch, dm, u, nullptr, nullptr, w, h1, h2, nullptr, false, nullptr, nullptr, 0, st)
 }
-void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, double h1, double h2, const SolverScal* sc, cudaStream_t st) {
-  NLK_FOR_N(axhelm_dispatch, dm, p, p, r, w, h1, h2, sc, true, st)
+void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, double h1, double h2, SolverScal* sc,
+                      double* pap_partial, unsigned int* pap_counter, int defer, cudaStream_t st) {
+  NLK_FOR_N(axhelm_dispatch, dm, p, p, r, w, h1, h2, sc, true, pap_partial, pap_counter, defer, st)
 }
 
 // ------------------------------------------------------------------------------------------------ K2 dssum

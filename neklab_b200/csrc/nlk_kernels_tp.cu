@@ -38,6 +38,8 @@ __device__ __forceinline__ double mat_at(const double* __restrict__ M, int idx) 
 
 // PI / PO: x-pitch (row length in doubles) of the input / output tile; 0 = dense.  An odd pitch makes the DIR = 0 stage
 // (consecutive threads one row apart) free of shared-memory bank conflicts.
+// (Sharing a pencil between two threads -- twice the warps, half the outputs each -- was measured slower: 3.4 -> 4.0 ms on
+// the 3-D convection kernel, the register file then limits the SM to fewer resident blocks or forces spills.)
 template <int MO, int MI, int DIR, bool ACC, int N0, int N1, int N2, int MAT = MAT_SMEM, int PI_ = 0, int PO_ = 0>
 __device__ __forceinline__ void contract_t(double* __restrict__ out, const double* __restrict__ in, const double* __restrict__ M) {
   constexpr int O0 = DIR == 0 ? MO : N0, O1 = DIR == 1 ? MO : N1, O2 = DIR == 2 ? MO : N2;
@@ -47,7 +49,7 @@ __device__ __forceinline__ void contract_t(double* __restrict__ out, const doubl
   constexpr int istr = DIR == 0 ? 1 : (DIR == 1 ? PI : PI * N1);
   constexpr int ostr = DIR == 0 ? 1 : (DIR == 1 ? PO : PO * O1);
   if constexpr (NPEN >= 32) {
-    for (int t = threadIdx.x; t < NPEN; t += blockDim.x) {
+    auto pencil = [&](int t) {
       const int a = t % P0, b = (t / P0) % P1, c = t / (P0 * P1);
       const int ibase = a + PI * (b + N1 * c), obase = a + PO * (b + O1 * c);
       double r[MI];
@@ -60,7 +62,13 @@ __device__ __forceinline__ void contract_t(double* __restrict__ out, const doubl
         for (int l = 0; l < MI; ++l) s += mat_at<MAT>(M, o * MI + l) * r[l];
         if (ACC) out[obase + o * ostr] += s; else out[obase + o * ostr] = s;
       }
-    }
+    };
+    // Every 3-D launch in this file uses blockDim.x >= min(256, largest pencil count) (tp_threads), so up to 256 pencils
+    // the "loop" is a single guarded trip.  Written as a loop, the compiler hoists the MO*MI loop-invariant operator
+    // entries into uniform registers, runs out of them and spills (ncu: 77% of the issued instructions were
+    // R2UR / MOV.SPILL / LDCU shuffles, 23% DFMA).
+    if constexpr (NPEN <= 256) { if (threadIdx.x < NPEN) pencil(threadIdx.x); }
+    else { for (int t = threadIdx.x; t < NPEN; t += blockDim.x) pencil(t); }
   } else {
     constexpr int TOT = O0 * O1 * O2;
     for (int idx = threadIdx.x; idx < TOT; idx += blockDim.x) {
@@ -86,8 +94,10 @@ __device__ __forceinline__ void prefetch_l2(const double* base, int ndoubles, in
   for (int off = t * 128; off < ndoubles * 8; off += nthreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
 }
 constexpr int PF_DIST = 296;     // elements ahead (~2 CTAs per SM)
+// 3-D block size: one thread per pencil of the largest stage, at most 256
+__host__ __device__ constexpr int tp_block_threads(int nmax) { return (nmax * nmax + 31) / 32 * 32 > 256 ? 256 : (nmax * nmax + 31) / 32 * 32; }
 static inline int tp_threads(int nmax, int d, int np) {
-  if (d == 3) { int t = ((nmax * nmax + 31) / 32) * 32; return t > 256 ? 256 : t; }
+  if (d == 3) return tp_block_threads(nmax);
   int t = ((np + 31) / 32) * 32; return t > 256 ? 256 : (t < 64 ? 64 : t);
 }
 
@@ -391,29 +401,42 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
   constexpr int PN = DIM == 3 ? (n | 1) : n, PM = DIM == 3 ? (m | 1) : m, npdP = PM * m * mz;
   double* TR = sDd + m * m; double* UF = TR + 3 * npdP; double* W1 = UF + npdP; double* W2 = W1 + npdP; double* ACC = W2 + npdP;
   const size_t e = blockIdx.x;
-  if (DIM == 3 && e + PF_DIST < gridDim.x) {
-    const size_t en = e + PF_DIST;
-    prefetch_l2(rxd + en * (size_t)(d * d) * npd, d * d * npd, threadIdx.x, blockDim.x);
-    for (int c = 0; c < d; ++c) prefetch_l2(C.p[c] + en * np1, np1, threadIdx.x, blockDim.x);
-    for (int f = 0; f < nf; ++f) prefetch_l2(u.p[f] + en * np1, np1, threadIdx.x, blockDim.x);
-  }
+  // (no L2 prefetch here: at 161 KB per element the look-ahead of one resident wave does not survive in L2 -- ncu showed
+  // a 10% hit rate and twice the DRAM reads.)  Instead the next field's nodal values are fetched into registers while the
+  // current field is being contracted: PRE values per thread, NT = the block size tp_threads() launches.
+  constexpr int NT = tp_block_threads(m);
+  constexpr int PRE = (np1 + NT - 1) / NT;
+  double pre[PRE];
+  auto fetch = [&](const double* src) {
+#pragma unroll
+    for (int q = 0; q < PRE; ++q) { const int i = threadIdx.x + q * NT; pre[q] = i < np1 ? src[i] : 0.0; }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int q = 0; q < PRE; ++q) { const int i = threadIdx.x + q * NT; if (i < np1) W1[(i % n) + PN * (i / n)] = pre[q]; }
+  };
+  if constexpr (DIM == 3) fetch(C.p[0] + e * np1);
   load_mat_t(sI, I1dg, m * n); load_mat_t(sIt, I1dtg, m * n); load_mat_t(sDd, Ddg, m * m);
   __syncthreads();
 #pragma unroll 1
   for (int c = 0; c < d; ++c) {
-    const double* cc = C.p[c] + e * np1;
-    for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[(i % n) + PN * (i / n)] = cc[i];
-    __syncthreads();
     if constexpr (DIM == 2) {
+      const double* cc = C.p[c] + e * np1;
+      for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = cc[i];
+      __syncthreads();
       contract_t<m, n, 0, false, n, n, 1, MAT_I1D>(W2, W1, sI);
       contract_t<m, n, 1, false, m, n, 1, MAT_I1D>(TR + c * npd, W2, sI);
     } else {
+      stage();
+      __syncthreads();
+      fetch((c + 1 < d ? C.p[c + 1] : u.p[0]) + e * np1);
       contract_t<m, n, 0, false, n, n, n, MAT_I1D, PN, PM>(W2, W1, sI);
       contract_t<m, n, 1, false, m, n, n, MAT_I1D, PM, PM>(W1, W2, sI);
       contract_t<m, n, 2, false, m, m, n, MAT_I1D, PM, PM>(TR + c * npdP, W1, sI);
     }
   }
   const double* rx = rxd + e * (size_t)(d * d) * npd;
+#pragma unroll 2
   for (int i = threadIdx.x; i < npd; i += blockDim.x) {
     const int ip = (i % m) + PM * (i / m);
     double cf[3] = {TR[ip], TR[npdP + ip], d == 3 ? TR[2 * npdP + ip] : 0.0};
@@ -428,8 +451,13 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
   __syncthreads();
 #pragma unroll 1
   for (int f = 0; f < nf; ++f) {
-    const double* uf = u.p[f] + e * np1;
-    for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[(i % n) + PN * (i / n)] = uf[i];
+    if constexpr (DIM == 2) {
+      const double* uf = u.p[f] + e * np1;
+      for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = uf[i];
+    } else {
+      stage();
+      if (f + 1 < nf) fetch(u.p[f + 1] + e * np1);
+    }
     __syncthreads();
     if constexpr (DIM == 2) {
       contract_t<m, n, 0, false, n, n, 1, MAT_I1D>(W2, W1, sI);
@@ -476,11 +504,6 @@ __global__ void k_convect_adj_t(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __res
   double* sI = sm; double* sIt = sI + m * n; double* sDd = sIt + m * n;
   double* AC = sDd + m * m; double* UF = AC + 3 * npdP; double* W1 = UF + npdP; double* W2 = W1 + npdP; double* CF = W2 + npdP;
   const size_t e = blockIdx.x;
-  if (DIM == 3 && e + PF_DIST < gridDim.x) {
-    const size_t en = e + PF_DIST;
-    prefetch_l2(rxd + en * (size_t)(d * d) * npd, d * d * npd, threadIdx.x, blockDim.x);
-    for (int c = 0; c < d; ++c) { prefetch_l2(cf.p[c] + en * np1, np1, threadIdx.x, blockDim.x); prefetch_l2(U.p[c] + en * np1, np1, threadIdx.x, blockDim.x); }
-  }
   load_mat_t(sI, I1dg, m * n); load_mat_t(sIt, I1dtg, m * n); load_mat_t(sDd, Ddg, m * m);
   for (int i = threadIdx.x; i < d * npdP; i += blockDim.x) AC[i] = 0.0;
   __syncthreads();

@@ -218,9 +218,8 @@ int helmholtz_solve(nlk_ctx* c, double* rhs, double h1, double h2, const double*
   int done = 0, it = 0;
   while (!done) {
     for (int b = 0; b < batch; ++b) {
-      launch_axhelm_cg(dm, c->cg_p, c->cg_r, c->cg_w, h1, h2, c->d_sc, c->st);
+      launch_axhelm_cg(dm, c->cg_p, c->cg_r, c->cg_w, h1, h2, c->d_sc, c->cg_pap_partial, c->cg_pap_counter, multi ? 1 : 0, c->st);   // w = H p, p.Hp
       if (ctx_gs(c, Ptr3{{c->cg_w, nullptr, nullptr}}, 1)) return 1;
-      launch_cg_pap(dm, c->cg_w, c->cg_p, mask, c->d_sc, c->red, multi ? 1 : 0, c->st);
       if (multi) { if (ctx_allreduce(c, c->d_sc->red + 2, 1, false)) return 1; launch_cg_finalize(c->d_sc, 1, dm.volvm1, c->st); }
       if (reduce_zr(0)) return 1;
     }
@@ -288,13 +287,16 @@ int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* it
       ++iter;
       double* vj = c->gm_V + (size_t)(j - 1) * N2; double* zj = c->gm_Z + (size_t)(j - 1) * N2;
       (void)tmp;
-      if (apply_precond(c, vj, zj, dm.mu)) return 1;                          // z = M^-1 (mu v)
-      if (ortho(c, zj)) return 1;
-      if (apply_E(c, zj, w, dm.ml)) return 1;                                 // w = ml * E z
-      launch_multidot(c->gm_V, N2, j, w, N2, dh, c->red, c->st);
-      if (ctx_allreduce(c, dh, j, false)) return 1;
-      launch_multiaxpy_norm(w, c->gm_V, N2, j, dh, -1.0, N2, dh + m, c->red, c->st);   // w -= V h ; |w|^2
-      if (ctx_allreduce(c, dh + m, 1, false)) return 1;
+      { PhaseScope ps(c->ph, PH_PRECOND, c->st);
+        if (apply_precond(c, vj, zj, dm.mu)) return 1;                        // z = M^-1 (mu v)
+        if (ortho(c, zj)) return 1; }
+      { PhaseScope ps(c->ph, PH_EAPPLY, c->st);
+        if (apply_E(c, zj, w, dm.ml)) return 1; }                             // w = ml * E z
+      { PhaseScope ps(c->ph, PH_ORTH, c->st);
+        launch_multidot(c->gm_V, N2, j, w, N2, dh, c->red, c->st);
+        if (ctx_allreduce(c, dh, j, false)) return 1;
+        launch_multiaxpy_norm(w, c->gm_V, N2, j, dh, -1.0, N2, dh + m, c->red, c->st);   // w -= V h ; |w|^2
+        if (ctx_allreduce(c, dh + m, 1, false)) return 1; }
       if (ctx_read_scalars(c, m + 1)) return 1;
       for (int i = 0; i < j; ++i) H[(size_t)i * m + (j - 1)] = c->h_red[i];
       for (int i = 0; i < j - 1; ++i) {
@@ -436,6 +438,7 @@ int step_advance(nlk_ctx* c, int istep) {
   const int nbd = std::min(istep, P.torder), nab = std::min(istep, 3);
   double bd[4], ab[3]; bdf_coeffs(nbd, bd); ab_coeffs(nab, nbd, ab);
   cudaStream_t st = c->st;
+  int ph = c->ph.begin(PH_MAKEF, st);
   // ---- igeom = 1: makefp = makeufp + advabp(_adjoint) + makextp + makebdfp ; lagfieldp
   for (int k = 0; k < d; ++k) {
     const double* f0 = (P.ifheat && P.buoyancy[k] != 0.0) ? c->tp : nullptr;
@@ -468,6 +471,7 @@ int step_advance(nlk_ctx* c, int istep) {
     ++nf;
   }
   launch_rhs_tail(dm, t, nf, ab[0], ab[1], ab[2], bd[1], bd[2], bd[3], st);
+  c->ph.end(ph, st); ph = c->ph.begin(PH_VRES, st);
   // ---- igeom = 2: velocity.  cresvipp
   const double h1 = P.viscosity, h2 = rho * bd[0] / dt;
   if (!c->nonlinear)    // bcdirvc: homogeneous for perturbations; the nonlinear state keeps its (inflow) boundary values
@@ -481,11 +485,13 @@ int step_advance(nlk_ctx* c, int istep) {
     launch_axhelm(dm, c->vp[k], c->wk[6], h1, h2, st);
     launch_lin(gp.p[k], dm.N1, 1.0, gp.p[k], 1.0, c->bf[k], -1.0, c->wk[6], 0, nullptr, nullptr, st);                           // res = Dtp* + bf - H u
   }
+  c->ph.end(ph, st); ph = c->ph.begin(PH_HELM, st);
   // ophinv: Jacobi-PCG on every component (one persistent launch for all of them when the problem is small)
   {
     double* rhsv[3] = {gp.p[0], gp.p[1], gp.p[2]}; const double* mk[3] = {dm.mask[0], dm.mask[1], dm.mask[2]}; double* solv[3] = {c->vp[0], c->vp[1], c->vp[2]};
     if (helmholtz_solve_multi(c, d, rhsv, h1, h2, mk, P.vtol, solv)) return 1;
   }
+  c->ph.end(ph, st); ph = c->ph.begin(PH_PRHS, st);
   // incomprp: E dp = -(bd1/dt) D u*, solved in the dt/bd1-scaled form (rhs = -D u*, dp = x * bd1/dt)
   double* rhs = c->pw[4];
   launch_opdiv(dm, CPtr3{{c->vp[0], c->vp[1], c->vp[2]}}, rhs, -1.0, st);
@@ -493,14 +499,18 @@ int step_advance(nlk_ctx* c, int istep) {
   NLK_CUDA(cudaMemcpyAsync(c->prlag, c->prp, dm.N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));                            // lagpresp
   NLK_CUDA(cudaMemcpyAsync(c->prp, pext, dm.N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));                                // up = prextr (+ dp below)
   double* xs = c->pw[3];                                                                                                        // pext is dead from here
+  c->ph.end(ph, st); ph = c->ph.begin(PH_PRES, st);
   if (pressure_solve_projected(c, rhs, P.ptol, xs, nullptr)) return 1;
+  c->ph.end(ph, st); ph = c->ph.begin(PH_CORR, st);
   launch_lin(c->prp, dm.N2, 1.0, c->prp, bd[0] / dt, xs, 0, nullptr, 0, nullptr, nullptr, st);                                  // add3(up, prextr, dp)
   Ptr3 w{{c->wk[0], c->wk[1], c->wk[2]}};
   launch_opgradt(dm, xs, w, st);
   if (ctx_gs(c, w, d)) return 1;
   for (int k = 0; k < d; ++k) launch_axpy_mm(c->vp[k], dm.N1, c->vp[k], 1.0 / rho, w.p[k], dm.binvm1, dm.mask[k], st);          // opbinv + opadd2cm
+  c->ph.end(ph, st);
   // ---- igeom = 2: temperature (cdscalp)
   if (P.ifheat) {
+    PhaseScope ps(c->ph, PH_HEAT, st);
     const double h1t = P.conductivity, h2t = P.rhocp * bd[0] / dt;
     launch_lin(c->tp, dm.N1, 1.0, c->tp, 0, nullptr, 0, nullptr, 0, nullptr, dm.mask[3], st);                                   // bcdirsc (homogeneous)
     launch_axhelm(dm, c->tp, c->wk[6], h1t, h2t, st);
@@ -512,8 +522,10 @@ int step_advance(nlk_ctx* c, int istep) {
   if (P.filter_weight > 0 && c->filterF) {
     Ptr4 fu{{c->vp[0], c->vp[1], d == 3 ? c->vp[2] : c->tp, c->tp}};
     int nfl = d + (P.ifheat ? 1 : 0);
+    PhaseScope ps(c->ph, PH_FILTER, st);
     launch_filter(dm, c->filterF, fu, nfl, st);
   }
+  c->ph.resolve(st);
   c->steps += 1;
   return 0;
 }
