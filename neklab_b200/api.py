@@ -106,12 +106,38 @@ def dense_eig(A):
     return wr, wi, VR
 
 
+def resolve_sym(coords, cbc):
+    """Rewrite 'SYM' boundary codes as 'SYx' / 'SYy' / 'SYz' (PHYSICAL normal of the symmetry plane, read off the
+    coordinates) -- unstructured meshes rotate their elements, so the plane's normal is not the element's reference axis.
+    coords: (E, ndim, nz, ny, nx) for the SAME elements as cbc (E, nface): call it on the global arrays before partitioning.
+    Only coordinate planes are supported (all the reference's configs: back_fstep `bfs.usr` usrdat, `setbc(4,1,'SYM')`)."""
+    cbc = np.array(cbc, dtype="U3")
+    coords = np.asarray(coords)
+    d = coords.shape[1]
+    s = slice(None)
+    faces = [(s, 0, s), (s, s, -1), (s, -1, s), (s, s, 0), (0, s, s), (-1, s, s)][:2 * d]
+    for f, sl in enumerate(faces):
+        idx = np.where(cbc[:, f] == "SYM")[0]
+        if not len(idx):
+            continue
+        ext = np.stack([np.ptp(coords[(idx, c) + sl].reshape(len(idx), -1), axis=1) for c in range(d)], axis=1)
+        ax = np.argmin(ext, axis=1)
+        if (ext[np.arange(len(idx)), ax] > 1e-8 * ext.max(axis=1)).any():
+            raise NlkError("a 'SYM' face is not a coordinate plane (general symmetry planes are not supported)")
+        cbc[idx, f] = np.array(["SYx", "SYy", "SYz"])[ax]
+    return cbc
+
+
 class Mesh:
-    """Host-side mesh (geometry + numbering).  coords: (E_local, ndim, nz, ny, nx); vertex: (E_global, 2**ndim)."""
+    """Host-side mesh (geometry + numbering).  coords: (E_local, ndim, nz, ny, nx); vertex: (E_global, 2**ndim).
+    'SYM' codes are resolved to physical axes here when the coordinates cover every element (single rank); multi-rank
+    callers run `resolve_sym` on the global arrays first."""
 
     def __init__(self, coords, vertex, cbc_v, lxd, cbc_t=None, gllnid=None, rank=0, nranks=1):
         L = lib()
         coords = _f64(coords)
+        if coords.shape[0] == np.asarray(vertex).shape[0]:
+            cbc_v = resolve_sym(coords, cbc_v)
         self.ndim = coords.shape[1]; self.lx1 = coords.shape[-1]; self.lxd = lxd
         self._x = [np.ascontiguousarray(coords[:, c]) for c in range(self.ndim)]
         self._vertex = np.ascontiguousarray(vertex, dtype=np.int64)

@@ -46,7 +46,19 @@ static void tensor_apply(const double* M, int mo, int mi, const double* u, doubl
 static inline bool is_dirichlet_v(const char* c) {
   return (c[0] == 'v' || c[0] == 'V' || c[0] == 'W' || c[0] == 'w') && (c[1] == ' ' || c[1] == 'l' || c[1] == 'L' || c[1] == 0);
 }
-static inline bool is_sym(const char* c) { return c[0] == 'S' && c[1] == 'Y' && c[2] == 'M'; }
+// 'SYM': symmetry plane whose normal is the element's own reference axis of that face (structured, unrotated meshes);
+// 'SYx' / 'SYy' / 'SYz': symmetry plane with PHYSICAL normal x / y / z -- what a front end writes for unstructured meshes
+// whose elements are rotated (api.resolve_sym does it from the coordinates).  Returns the velocity component to mask, -1 if
+// the code is not a symmetry code.  (Nek's general 'SYM' rotates into face-normal coordinates; only axis-aligned planes
+// occur in the reference's configs.)
+static inline int sym_axis(const char* c, int ref_axis) {
+  if (c[0] != 'S' || c[1] != 'Y') return -1;
+  if (c[2] == 'M') return ref_axis;
+  if (c[2] == 'x' || c[2] == 'X') return 0;
+  if (c[2] == 'y' || c[2] == 'Y') return 1;
+  if (c[2] == 'z' || c[2] == 'Z') return 2;
+  return -1;
+}
 static inline bool is_outflow(const char* c) { return (c[0] == 'O' || c[0] == 'o'); }
 static inline bool is_dirichlet_t(const char* c) { return (c[0] == 't' || c[0] == 'T') && (c[1] == ' ' || c[1] == 0); }
 
@@ -95,6 +107,29 @@ int build_mesh(HostMesh& hm, int ndim, int lx1, int lxd, int64_t nelg, int64_t n
   }
   hm.has_outflow = false;
   for (int64_t e = 0; e < nelg; ++e) for (int f = 0; f < nf; ++f) if (is_outflow(cbc_v + ((size_t)e * nf + f) * 3)) hm.has_outflow = true;
+  // symmetry planes must be coordinate planes of the masked component: check every local symmetry face geometrically
+  for (int64_t e = 0; e < E; ++e) for (int f = 0; f < nf; ++f) {
+    const char* s = cbc_v + ((size_t)hm.lglel[e] * nf + f) * 3;
+    const int ax = FACE_AXIS[f], side = FACE_SIDE[f], sa = sym_axis(s, ax);
+    if (sa < 0) continue;
+    if (sa >= d) { set_error("symmetry code names an axis outside the mesh dimension"); return 1; }
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, elo = 1e300, ehi = -1e300;
+    const int nz = d == 3 ? n : 1;
+    for (int k = 0; k < nz; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+      const size_t g = (size_t)e * np1 + ((size_t)k * n + j) * n + i;
+      for (int c = 0; c < d; ++c) { elo = std::min(elo, hm.xyz[c][g]); ehi = std::max(ehi, hm.xyz[c][g]); }
+      const int idx = ax == 0 ? i : (ax == 1 ? j : k);
+      if (idx != (side ? n - 1 : 0)) continue;
+      for (int c = 0; c < d; ++c) { lo[c] = std::min(lo[c], hm.xyz[c][g]); hi[c] = std::max(hi[c], hm.xyz[c][g]); }
+    }
+    double ext = 0; for (int c = 0; c < d; ++c) ext = std::max(ext, hi[c] - lo[c]);
+    if (hi[sa] - lo[sa] > 1e-8 * std::max(ext, 1e-300)) {
+      set_error("symmetry face is not a coordinate plane of the masked component: write 'SYx'/'SYy'/'SYz' (physical normal) in the "
+                "boundary codes (neklab_b200.api.resolve_sym) -- plain 'SYM' means the element's own reference axis");
+      return 1;
+    }
+    (void)elo; (void)ehi;
+  }
 
   // ---- geometry
   const size_t N1 = (size_t)E * np1, N2 = (size_t)E * np2, Nd = (size_t)E * npd;
@@ -236,7 +271,7 @@ int build_mesh(HostMesh& hm, int ndim, int lx1, int lxd, int64_t nelg, int64_t n
       uint8_t bits = 0;
       int ax = FACE_AXIS[f], side = FACE_SIDE[f];
       if (is_dirichlet_v(cv)) bits |= 7;
-      if (is_sym(cv)) bits |= (uint8_t)(1 << ax);
+      { const int sa = sym_axis(cv, ax); if (sa >= 0 && sa < d) bits |= (uint8_t)(1 << sa); }
       if (cbc_t && is_dirichlet_t(cbc_t + ((size_t)e * nf + f) * 3)) bits |= 8;
       if (!bits) continue;
       for (int c = 0; c < nv; ++c) if (((c >> ax) & 1) == side) vbits[vertex_all[e * nv + c]] |= bits;

@@ -305,10 +305,20 @@ class SEMesh:
         for f in range(2 * d):
             sl = face_slices(f, d)
             dirich = np.isin(cbc[:, f], DIRICHLET_VEL)
-            # SYM: zero the face-normal component on axis-aligned faces
-            sym = np.isin(cbc[:, f], ("SYM",))
-            normal_axis = {0: 1, 1: 0, 2: 1, 3: 0, 4: 2, 5: 2}[f]
-            fix = dirich | (sym & (normal_axis == comp))
+            # SYM (Nek `bcmask`, axis-aligned symmetry planes only): zero the component along the face's PHYSICAL normal,
+            # found from the coordinates (unstructured meshes rotate their elements); 'SYx'/'SYy'/'SYz' name it explicitly
+            codes = np.char.upper(cbc[:, f].astype(str))
+            sym = np.char.startswith(codes, "SY")
+            fix = dirich.copy()
+            if sym.any():
+                ext = np.stack([np.ptp(self.coords[(slice(None), c) + sl].reshape(len(cbc), -1), axis=1) for c in range(d)], axis=1)
+                phys = np.argmin(ext, axis=1)
+                explicit = np.array([{"X": 0, "Y": 1, "Z": 2}.get(s[2:3], -1) for s in codes])
+                bad = sym & (explicit < 0) & (ext[np.arange(len(cbc)), phys] > 1e-8 * ext.max(axis=1))
+                if bad.any():
+                    raise ValueError("SYM face is not a coordinate plane")
+                axis = np.where(explicit >= 0, explicit, phys)
+                fix |= sym & (axis == comp)
             idx = np.where(fix)[0]
             if len(idx):
                 m[(idx,) + sl] = 0.0

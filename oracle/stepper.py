@@ -324,10 +324,30 @@ class PertStepper:
     def _solve_pressure(self, rhs, tol):
         m = self.mesh
         if self.prm.pressure_solver == "direct":
+            import scipy.sparse.linalg as spl
+            N = rhs.size
             if self._lu_E is None:
-                import scipy.sparse.linalg as spl
-                self._lu_E = spl.splu(assemble_E(m, self.prm.density))
-            return ops.ortho(m, self._lu_E.solve(rhs.ravel()).reshape(rhs.shape))
+                E = assemble_E(m, self.prm.density)
+                lu = spl.splu(E)
+                # no outflow: E has the constants in its (near-)null space -- exactly on straight-sided meshes, to quadrature
+                # error on curved ones (bfs: |E 1| = 6e-5) -- and Nek's uzawa_gmres only ever moves in mean-free directions
+                # (`ortho`).  The converged limit of that iteration is the solution of the bordered system
+                #   [E 1; 1^T 0] [x; mu] = [rhs; 0],
+                # solved here by block elimination with the LU of E (w = E^-1 1) plus iterative refinement on the bordered residual.
+                w = None if m.has_outflow else lu.solve(np.ones(N))
+                self._lu_E = (E, lu, w)
+            E, lu, w = self._lu_E
+            b = rhs.ravel()
+            if w is None:
+                return lu.solve(b).reshape(rhs.shape)
+            sw = w.sum()
+            x = np.zeros(N); mu = 0.0
+            for _ in range(4):
+                r = b - E @ x - mu; s_ = -x.sum()
+                y = lu.solve(r)
+                dmu = (y.sum() - s_) / sw
+                x += y - dmu * w; mu += dmu
+            return x.reshape(rhs.shape)
         pre = self._precond if self._precond is not None else (lambda r: r / m.bm2)
         return uzawa_gmres(m, rhs, self._apply_E, pre, tol, self.prm.gmres_maxit, self.prm.lgmres, self.stats)
 

@@ -49,6 +49,55 @@ def test_cylinder_mesh_numbering_bit_exact(nlk_lib):
     assert m.info.nvert == 2033 and m.info.nglob_local == 50089
 
 
+def test_bfs_mesh_numbering_and_symmetry_masks(nlk_lib):
+    """Second reference mesh (examples/back_fstep, gmsh, rotated elements): numbering bit-exact, masks equal to the oracle's;
+    a plain 'SYM' on a face whose physical normal is not the element's reference axis is rejected instead of mis-masked."""
+    from neklab_b200 import api
+    from tests.util import bfs_case
+    om, bf, prm, z = bfs_case()
+    m = nlk_mesh(om)                                    # api.Mesh resolves 'SYM' -> 'SYx'/'SYy' from the coordinates
+    assert np.array_equal(m.glo_num(), om.glo)
+    assert m.info.nglob_local == om.nglob == 69696 and not m.info.has_outflow
+    for c in range(2):
+        assert np.array_equal(m.field(f"vmask{c}"), om.vmask[c])
+    res = api.resolve_sym(om.coords, z["cbc"])
+    assert set(np.unique(res[z["cbc"] == "SYM"]).tolist()) == {"SYy"}
+    # multi-rank entry (local coordinates, no auto-resolution): the resolved codes give the same masks and numbering
+    gll = api.partition(z["pid"], 2); sel = np.where(gll == 0)[0]
+    m0 = api.Mesh(om.coords[sel], om.vertex, res, 9, gllnid=gll, rank=0, nranks=2)
+    assert np.array_equal(m0.field("vmask1"), om.vmask[1][sel]) and np.array_equal(m0.glo_num(), om.glo[sel])
+
+
+def test_symmetry_code_on_a_rotated_element(nlk_lib):
+    """One element turned by 90 degrees (x = 1 - s, y = r): its reference face 0 (s = -1) is the physical plane x = 1.  A plain
+    'SYM' there would mask the wrong component, so the library refuses it when it cannot resolve the axis itself, and the
+    resolved code 'SYx' masks v_x."""
+    from neklab_b200 import api
+    from neklab_b200.boxmesh import gll_points
+    n = 5
+    g = 0.5 * (np.asarray(gll_points(n)) + 1.0)
+    coords = np.zeros((1, 2, 1, n, n))
+    coords[0, 0, 0] = 1.0 - g[:, None]              # x[j, i] = 1 - s_j
+    coords[0, 1, 0] = g[None, :]                    # y[j, i] = r_i
+    vertex = np.array([[1, 2, 3, 4]], dtype=np.int64)
+    cbc = np.array([["SYM", "W  ", "W  ", "W  "]])
+    d = api.MeshDesc(2, n, 8, 1, 1, api._p(np.ascontiguousarray(coords[:, 0])), api._p(np.ascontiguousarray(coords[:, 1])), None,
+                     api._p(vertex), api._p(api.cbc_bytes(cbc)), None, None, 0, 1)
+    h = api.C.c_void_p()
+    assert api.lib().nlk_mesh_create(api.C.byref(d), api.C.byref(h)) != 0          # raw C-ABI call with the ambiguous code
+    assert b"symmetry" in api.lib().nlk_last_error()
+    res = api.resolve_sym(coords, cbc)
+    assert res[0, 0] == "SYx"
+    m = api.Mesh(coords, vertex, cbc, 8)                                             # the Python front end resolves it
+    mx, my = m.field("vmask0"), m.field("vmask1")
+    face = np.isclose(coords[:, 0], 1.0)
+    inner = face & (coords[:, 1] > 1e-9) & (coords[:, 1] < 1 - 1e-9)                 # away from the wall corners
+    assert mx[inner].max() == 0.0 and my[inner].min() == 1.0
+    from oracle.mesh import SEMesh
+    om = SEMesh(coords, vertex, cbc, 8)
+    assert np.array_equal(om.vmask[0], mx) and np.array_equal(om.vmask[1], my)
+
+
 def test_partition_rule(nlk_lib):
     from neklab_b200 import api
     z = cylinder_case()[3]

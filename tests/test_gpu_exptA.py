@@ -156,3 +156,39 @@ def test_boussinesq_filter_parity(nlk_lib):
     assert yd.get_size() == y_or.size()
     assert abs(yd.dot(yd) - y_or.dot(y_or)) < 1e-9 * y_or.dot(y_or)      # theta enters the inner product
     ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------- reference config C4
+def test_back_fstep_matvec_parity(nlk_lib):
+    """examples/back_fstep/transient_growth from the committed fixture (2 760 gmsh elements, lx1 = 6, Re = 600, bdf2, explicit
+    filter 0.01/0.84, walls 'W', inlet and outlet 'v', free-slip 'SYM' planes, singular pressure operator): a short direct and
+    adjoint exptA apply (4 steps + 1 restart step) against the oracle with sparse-direct inner solves."""
+    from neklab_b200 import api
+    from tests.util import bfs_case
+    om, bf, prm, z = bfs_case()
+    prm.pressure_solver = "direct"; prm.helm_solver = "direct"
+    st = PertStepper(om, prm)
+    A_or = ExptA(st, 18.0, bf)
+    dt, nsteps = A_or.init()
+    assert nsteps == 1933                                        # SURVEY.md C4
+    A_or.tau = 4 * dt + 1e-12
+    m = nlk_mesh(om)
+    ctx = api.Context(m, api.default_params(viscosity=1.0 / 600.0, torder=2, vtol=1e-13, ptol=1e-13, filter_weight=0.01, filter_cutoff=0.84,
+                                            gmres_maxit=3000, cg_maxit=3000, pr_proj=8))
+    A = api.exptA_linop(ctx, 18.0, _to_dev(ctx, bf))
+    s = A.init()
+    assert s["nsteps"] == 1933 and abs(s["dt"] - dt) < 1e-15
+    api.lib().nlk_exptA_set_tau(A.h, __import__("ctypes").c_double(4 * dt + 1e-12))
+    x0 = seeded_field(om, 7, torder=2)
+    for name in ("matvec", "rmatvec"):
+        y_or = getattr(A_or, name)(x0)
+        yd = getattr(A, name)(_to_dev(ctx, x0))
+        v, pr, _ = yd.download()
+        err = _wnorm(om, [v[c] - y_or.v[c] for c in range(2)]) / _wnorm(om, y_or.v)
+        assert err < 1e-9, (name, err)                           # iterative (1e-13) vs sparse-direct inner solves
+        assert yd.nrst == 1 == y_or.nrst
+        assert A.stats()["nsteps"] == 4
+        # free-slip planes: v_y = 0, v_x free
+        top = np.isclose(om.coords[:, 1], 20.0) & (om.coords[:, 0] > -19.9) & (om.coords[:, 0] < 99.9)
+        assert np.abs(v[1][top]).max() == 0.0 and np.abs(v[0][top]).max() > 0.0
+    ctx.close()

@@ -81,3 +81,44 @@ def test_golden_eigenvalue_pin():
     if os.path.exists(p):
         con = json.load(open(p))
         assert abs(con["modulus"][0] - 1.0156) < 2.5e-4
+
+
+# ---- second reference fixture: examples/back_fstep/transient_growth (gmsh mesh with rotated elements, 'SYM' planes) ----
+@pytest.fixture(scope="module")
+def bfs():
+    from tests.util import bfs_case
+    return bfs_case()
+
+
+def test_bfs_cfl_gives_the_reference_step_count(bfs):
+    """`setup_nek` rule (src/neklab_nek_setup.f90:193-224): dt = 0.5/ctarg, nsteps = ceil(tau/dt).  SURVEY.md C4 quotes
+    nsteps = 1933 for tau = 18 -- reproduced from the shipped base flow by the oracle's compute_cfl."""
+    om, bf, prm, z = bfs
+    ctarg = ops.compute_cfl(om, bf.v, 1.0)
+    assert int(np.ceil(18.0 / (0.5 / ctarg))) == 1933
+
+
+def test_bfs_numbering_partition_and_divergence(bfs):
+    om, bf, prm, z = bfs
+    assert om.nglob == 69696 and sorted(np.unique(om.mult_count).tolist()) == [1, 2, 4]
+    assert same_partition(om.glo, glo_num_from_coords(om.coords, periods={}))        # .ma2 ids are coordinate-consistent
+    assert np.bincount(partition_rank(z["pid"], 2)).tolist() == [1380, 1380]
+    assert np.bincount(partition_rank(z["pid"], 8)).tolist() == [345] * 8
+    # the base flow is stored in single precision: weakly divergence-free to f32 round-off
+    div = ops.opdiv(om, bf.v)
+    assert np.sqrt((div * div / om.bm2).sum() / om.bm2.sum()) < 1e-6
+    assert not om.has_outflow                                                        # inlet and outlet are both 'v'
+
+
+def test_bfs_symmetry_masks_follow_the_physical_normal(bfs):
+    """The gmsh mesh rotates its elements: the free-slip planes y = 1 (x < 0) and y = 20 must mask v_y and leave v_x free
+    whatever the element's reference orientation (Nek `bcmask` for 'SYM')."""
+    om, bf, prm, z = bfs
+    x, y = om.coords[:, 0], om.coords[:, 1]
+    top = np.isclose(y, 20.0) & (x > -19.9) & (x < 99.9)
+    assert top.sum() > 500 and om.vmask[1][top].max() == 0.0 and om.vmask[0][top].min() == 1.0
+    wall = np.isclose(y, 0.0) & (x > 0.1) & (x < 99.9)
+    assert om.vmask[0][wall].max() == 0.0 and om.vmask[1][wall].max() == 0.0
+    # faces of one physical plane sit on different reference faces
+    ref_faces = {f for f in range(4) if (z["cbc"][:, f] == "SYM").any()}
+    assert len(ref_faces) > 1

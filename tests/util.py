@@ -57,6 +57,18 @@ def cylinder_case():
     return om, bf, prm, z
 
 
+def bfs_case():
+    """examples/back_fstep/transient_growth (Re=600, lx1=6, lxd=9, bdf2, tau=18, filter 0.01/0.84; boundary codes from
+    bfs.usr `usrdat`: wall 'W', inlet AND outlet 'v', free-slip 'SYM') from the committed fixture."""
+    z = np.load(os.path.join(GOLDEN, "bfs_case.npz"))
+    om = SEMesh(z["coords"], z["vertex"], z["cbc"], 9)
+    bf = NekVec(om, 2)
+    bf.v = [z["vel"][:, 0].copy(), z["vel"][:, 1].copy()]
+    bf.pr = ops.map12(om, z["pr"])
+    prm = StepParams(viscosity=1.0 / 600.0, torder=2, vtol=1e-8, ptol=1e-6, filter_weight=0.01, filter_cutoff=0.84)
+    return om, bf, prm, z
+
+
 def smooth_fields(om: SEMesh, k, seed=0):
     rng = np.random.default_rng(seed)
     x = om.coords
