@@ -91,3 +91,23 @@ def test_krylov_schur_small_matrix():
     lam, res, X, Y, k = eigs(lambda v: V(M @ v.a), V(rng.standard_normal(n)), nev=3, kdim=20, tol=1e-10, maxiter=50)
     ref = np.linalg.eigvals(M); ref = ref[np.argsort(-np.abs(ref))]
     assert np.abs(np.sort(np.abs(lam[:3])) - np.sort(np.abs(ref[:3]))).max() < 1e-8
+
+
+def test_direct_mode_without_outflow_solves_the_bordered_system():
+    """No outflow: the pressure operator has the constants in its (near-)null space and uzawa_gmres moves only in mean-free
+    directions; the sparse-direct mode must give the same converged limit -- on a straight-sided box (E exactly singular) and
+    on a warped one, where the weak divergence is integrated inexactly and E 1 != 0 (the back_fstep situation)."""
+    from oracle.stepper import uzawa_gmres
+    for warp in (False, True):
+        om, _, _ = box_case(ndim=2, nel=(4, 4), n=6, lxd=9, warp=warp)          # walls all round
+        assert not om.has_outflow
+        rng = np.random.default_rng(3)
+        u = [om.vmask[c] * rng.standard_normal(om.bm1.shape) for c in range(2)]
+        rhs = ops.ortho(om, -ops.opdiv(om, u))
+        st = PertStepper(om, StepParams(viscosity=0.05, pressure_solver="direct"))
+        xd = st._solve_pressure(rhs, 0.0)
+        assert abs(xd.mean()) < 1e-13
+        xg = uzawa_gmres(om, rhs, lambda p: ops.cdabdtp(om, p, 1.0), SchwarzCoarse(om), 1e-14, 3000, 30, {})
+        assert np.abs(xd - xg).max() < 1e-9 * np.abs(xg).max(), warp
+        r = ops.cdabdtp(om, xd, 1.0) - rhs
+        assert np.abs(ops.ortho(om, r)).max() < 1e-10 * np.abs(rhs).max()       # residual is a multiple of the constant
