@@ -117,7 +117,6 @@ void launch_cg_init(const DevMesh& dm, SolverScal* sc, double tol, int maxit, cu
 // defer != 0: only store the local sums in sc->red[] (multi-rank: allreduce, then launch_cg_finalize)
 void launch_cg_update_reduce(const DevMesh& dm, double* x, double* r, const double* p, const double* w, const double* mask,
                              double h1, double h2, SolverScal* sc, Reducer red, int first, int defer, cudaStream_t st);
-void launch_cg_pap(const DevMesh& dm, const double* w, const double* p, const double* mask, SolverScal* sc, Reducer red, int defer, cudaStream_t st);
 // reductions: out[0..nout) = sum_i a_i*b_i*(c_i)  for up to 4 (a,b) pairs sharing weight c (nullable)
 void launch_dot(size_t n, CPtr4 a, CPtr4 b, int npairs, const double* c, double* out, Reducer red, cudaStream_t st);
 // K9  multi-dot h[j] = sum_i V[j][i]*w[i], j<k (uzawa_gmres CGS) and w -= sum_j h[j] V[j]

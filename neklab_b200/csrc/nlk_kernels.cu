@@ -682,19 +682,6 @@ void launch_cg_update_reduce(const DevMesh& dm, double* x, double* r, const doub
   k_cg_update_reduce<<<grid, RED_THREADS, 0, st>>>(x, r, p, w, mask, dm.diagA, dm.diagB, dm.vmult, dm.binvm1, h1, h2, dm.volvm1, dm.N1, sc, red, first, defer);
   LAUNCH_COUNT();
 }
-__global__ void __launch_bounds__(256)
-k_cg_pap(const double* __restrict__ w, const double* __restrict__ p, const double* __restrict__ mask, const double* __restrict__ mult,
-         size_t n, SolverScal* sc, Reducer red, int defer) {
-  if (sc->done) return;
-  double v[1] = {0.0};
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[0] += w[i] * mask[i] * p[i] * mult[i];
-  if (grid_reduce<1>(v, red)) { sc->red[2] = v[0]; if (!defer) cg_finalize_pap(sc); }
-}
-void launch_cg_pap(const DevMesh& dm, const double* w, const double* p, const double* mask, SolverScal* sc, Reducer red, int defer, cudaStream_t st) {
-  int grid = stream_grid(dm.N1, RED_BLOCKS);
-  k_cg_pap<<<grid, RED_THREADS, 0, st>>>(w, p, mask, dm.vmult, dm.N1, sc, red, defer); LAUNCH_COUNT();
-}
-
 // ------------------------------------------------------------------------------------------------ dots
 template <int NP, bool W>
 __global__ void __launch_bounds__(256)

@@ -267,7 +267,7 @@ int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* it
   const DevMesh& dm = c->dm;
   const int m = c->prm.lgmres, maxit = c->prm.gmres_maxit;
   const size_t N2 = dm.N2;
-  double* r = c->pw[0]; double* w = c->pw[1]; double* tmp = c->pw[2];
+  double* r = c->pw[0]; double* w = c->pw[1];
   const double norm_fac = 1.0 / std::sqrt(dm.volvm2);
   std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gamma(m + 2), cc(m);
   launch_fill(x, N2, 0.0, c->st);
@@ -286,7 +286,6 @@ int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* it
     for (j = 1; j <= m; ++j) {
       ++iter;
       double* vj = c->gm_V + (size_t)(j - 1) * N2; double* zj = c->gm_Z + (size_t)(j - 1) * N2;
-      (void)tmp;
       { PhaseScope ps(c->ph, PH_PRECOND, c->st);
         if (apply_precond(c, vj, zj, dm.mu)) return 1;                        // z = M^-1 (mu v)
         if (ortho(c, zj)) return 1; }
