@@ -114,6 +114,8 @@ struct nlk_ctx {
   bool coarse_sparse = false; int crs_iters = 0; int64_t crs_nnz = 0;
   int32_t* crs_rowptr = nullptr; int32_t* crs_col = nullptr; double* crs_val = nullptr; double* crs_dinv = nullptr;
   double* crs_p = nullptr, *crs_q = nullptr, *crs_z = nullptr, *crs_rr = nullptr;
+  double* cg_hd[4] = {nullptr, nullptr, nullptr, nullptr}, *cg_wa[4] = {nullptr, nullptr, nullptr, nullptr}, *cg_wb[4] = {nullptr, nullptr, nullptr, nullptr};
+  double cg_key_h1[4] = {0, 0, 0, 0}, cg_key_h2[4] = {0, 0, 0, 0};           // (h1, h2) the weights of mask slot k were built for (lazily allocated)
   double* cg_pap_partial = nullptr; unsigned int* cg_pap_counter = nullptr;   // block partials of p.Ap reduced inside the Helmholtz kernel
   double* crs_partial = nullptr;         // per-block partial sums of the coarse PCG (own scratch: the solve runs on the side stream)
   cudaGraphExec_t crs_graph = nullptr; const double* crs_graph_in = nullptr; double* crs_graph_out = nullptr;   // the fixed-count PCG as one graph launch

@@ -93,8 +93,10 @@ bool launch_cg_persistent(const DevMesh& dm, CgArgs& a, cudaStream_t st);
 //     p = r*dinv + beta*p is fused in front (u is then p, read-modify-write), with dinv = 1/(h1*diagA+h2*diagB).
 void launch_axhelm(const DevMesh& dm, const double* u, double* w, double h1, double h2, cudaStream_t st);
 // pap_partial: one double per launched block (>= number of elements); with defer != 0 only sc->red[2] is stored (multi-rank)
-void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, double h1, double h2, SolverScal* sc,
+void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, const double* hd, double h1, double h2, SolverScal* sc,
                       double* pap_partial, unsigned int* pap_counter, int defer, cudaStream_t st);
+// per-(h1,h2) PCG weights: hd = mask/(h1 diagA + h2 diagB), wa = hd*mult, wb = mask*mult*binv
+void launch_cg_weights(const DevMesh& dm, const double* mask, double h1, double h2, double* hd, double* wa, double* wb, cudaStream_t st);
 // K2  dssum (gs_op add) on up to 3 fields; local part.
 void launch_gs(const DevMesh& dm, Ptr3 f, int nf, cudaStream_t st);
 // generic pointwise: out = (a0*x0 + a1*x1 + a2*x2 + a3*x3) * (mul ? mul : 1)
@@ -115,8 +117,8 @@ void launch_rhs_tail(const DevMesh& dm, const RhsTail& t, int nf, double ab0, do
 // K8  CG vector phases (cggo)
 void launch_cg_init(const DevMesh& dm, SolverScal* sc, double tol, int maxit, cudaStream_t st);
 // defer != 0: only store the local sums in sc->red[] (multi-rank: allreduce, then launch_cg_finalize)
-void launch_cg_update_reduce(const DevMesh& dm, double* x, double* r, const double* p, const double* w, const double* mask,
-                             double h1, double h2, SolverScal* sc, Reducer red, int first, int defer, cudaStream_t st);
+void launch_cg_update_reduce(const DevMesh& dm, double* x, double* r, const double* p, const double* w, const double* wa, const double* wb,
+                             SolverScal* sc, Reducer red, int first, int defer, cudaStream_t st);
 // reductions: out[0..nout) = sum_i a_i*b_i*(c_i)  for up to 4 (a,b) pairs sharing weight c (nullable)
 void launch_dot(size_t n, CPtr4 a, CPtr4 b, int npairs, const double* c, double* out, Reducer red, cudaStream_t st);
 // K9  multi-dot h[j] = sum_i V[j][i]*w[i], j<k (uzawa_gmres CGS) and w -= sum_j h[j] V[j]

@@ -94,7 +94,7 @@ static void ensure_const_D(const DevMesh& dm, cudaStream_t st) {
 }
 __device__ __forceinline__ void cg_finalize_pap(SolverScal* sc);
 // One element per (threadIdx.y) slice; thread (i,j) owns the k-column of the element (register-tiled k-loop, 3-D).
-// FUSE_CG: the CG search-direction update p = r/(h1*diagA+h2*diagB) + beta*p is applied while loading, and p.Ap is reduced
+// FUSE_CG: the CG search-direction update p = hd*r + beta*p (hd: masked inverse Jacobi diagonal) is applied while loading, and p.Ap is reduced
 // on the way out: p is continuous and masked, so the sum over local copies of p * w(unassembled) equals the assembled,
 // multiplicity-weighted inner product Nek's cggo takes after dssum -- one full pass over w, p, mask and mult saved per
 // iteration.  Block partials -> last block sums them in a fixed order (deterministic).
@@ -102,7 +102,7 @@ template <int N, int DIM, bool FUSE_CG>
 __global__ void __launch_bounds__(N * N * (N * N >= 100 ? 1 : (N * N >= 64 ? 2 : 4)), (N == 8 ? 8 : 1))
 k_axhelm(const double* __restrict__ u, double* __restrict__ pio, const double* __restrict__ r, double* __restrict__ w,
          const double* __restrict__ G, const double* __restrict__ bm1, const double* __restrict__ Dg,
-         const double* __restrict__ diagA, const double* __restrict__ diagB, double h1, double h2,
+         const double* __restrict__ hd, double h1, double h2,
          SolverScal* __restrict__ sc, int64_t E, double* __restrict__ pap_partial, unsigned int* pap_counter, int defer) {
   constexpr int NZ = DIM == 3 ? N : 1;
   constexpr int NN = N * N;
@@ -124,7 +124,7 @@ k_axhelm(const double* __restrict__ u, double* __restrict__ pio, const double* _
 #pragma unroll
     for (int k = 0; k < NZ; ++k) {
       size_t g = eb + k * NN + tid;
-      double z = r[g] / (h1 * diagA[g] + h2 * diagB[g]);
+      double z = r[g] * hd[g];                    // hd = mask / (h1 diagA + h2 diagB), precomputed per (h1, h2) (k_cg_weights)
       double pv = z + beta * pio[g];
       ru[k] = active ? pv : 0.0;
       if (active) pio[g] = pv;
@@ -218,13 +218,13 @@ k_axhelm(const double* __restrict__ u, double* __restrict__ pio, const double* _
 }
 
 template <int N, int DIM>
-static void axhelm_dispatch(const DevMesh& dm, const double* u, double* pio, const double* r, double* w, double h1, double h2,
+static void axhelm_dispatch(const DevMesh& dm, const double* u, double* pio, const double* r, double* w, const double* hd, double h1, double h2,
                             SolverScal* sc, bool fuse, double* pap_partial, unsigned int* pap_counter, int defer, cudaStream_t st) {
   constexpr int EPB = N * N >= 100 ? 1 : (N * N >= 64 ? 2 : 4);
   ensure_const_D(dm, st);
   dim3 block(N * N, EPB), grid(cdiv(dm.E, EPB));
-  if (fuse) k_axhelm<N, DIM, true><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, dm.diagA, dm.diagB, h1, h2, sc, dm.E, pap_partial, pap_counter, defer);
-  else k_axhelm<N, DIM, false><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, dm.diagA, dm.diagB, h1, h2, nullptr, dm.E, nullptr, nullptr, 0);
+  if (fuse) k_axhelm<N, DIM, true><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, hd, h1, h2, sc, dm.E, pap_partial, pap_counter, defer);
+  else k_axhelm<N, DIM, false><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, nullptr, h1, h2, nullptr, dm.E, nullptr, nullptr, 0);
   LAUNCH_COUNT();
 }
 
@@ -243,11 +243,11 @@ static void axhelm_dispatch(const DevMesh& dm, const double* u, double* pio, con
   }
 
 void launch_axhelm(const DevMesh& dm, const double* u, double* w, double h1, double h2, cudaStream_t st) {
-  NLK_FOR_N(axhelm_dispatch, dm, u, nullptr, nullptr, w, h1, h2, nullptr, false, nullptr, nullptr, 0, st)
+  NLK_FOR_N(axhelm_dispatch, dm, u, nullptr, nullptr, w, nullptr, h1, h2, nullptr, false, nullptr, nullptr, 0, st)
 }
-void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, double h1, double h2, SolverScal* sc,
+void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, const double* hd, double h1, double h2, SolverScal* sc,
                       double* pap_partial, unsigned int* pap_counter, int defer, cudaStream_t st) {
-  NLK_FOR_N(axhelm_dispatch, dm, p, p, r, w, h1, h2, sc, true, pap_partial, pap_counter, defer, st)
+  NLK_FOR_N(axhelm_dispatch, dm, p, p, r, w, hd, h1, h2, sc, true, pap_partial, pap_counter, defer, st)
 }
 
 // ------------------------------------------------------------------------------------------------ K2 dssum
@@ -649,12 +649,27 @@ __global__ void k_cg_init(SolverScal* sc, double tol, int maxit) {
 }
 void launch_cg_init(const DevMesh&, SolverScal* sc, double tol, int maxit, cudaStream_t st) { k_cg_init<<<1, 1, 0, st>>>(sc, tol, maxit); LAUNCH_COUNT(); }
 
-// x += alpha p ; r -= alpha (mask w)   [skipped when first]; then rtz1 = sum r*z*mult, rbn2 = sum r*r*mult*binv with
-// z = r/(h1 diagA + h2 diagB).  Finaliser applies Nek cggo's convergence test and sets beta.
+// Per-(h1,h2) weights of the streamed PCG, so that its two per-iteration kernels read three arrays instead of seven:
+//   hd = mask / (h1 diagA + h2 diagB)   (masked inverse Jacobi diagonal: z = hd r, so p and x stay 0 on Dirichlet nodes and
+//                                        r needs no masking there -- whatever accumulates in r on those nodes is never used)
+//   wa = hd * mult                      (r.z   = sum r^2 wa)
+//   wb = mask * mult * binv             (rbn2^2 = sum r^2 wb / vol, Nek cggo's convergence norm)
+__global__ void k_cg_weights(size_t n, const double* __restrict__ mask, const double* __restrict__ diagA, const double* __restrict__ diagB,
+                             const double* __restrict__ mult, const double* __restrict__ binv, double h1, double h2,
+                             double* __restrict__ hd, double* __restrict__ wa, double* __restrict__ wb) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double m = mask[i], d = m / (h1 * diagA[i] + h2 * diagB[i]), mu = mult[i];
+    hd[i] = d; wa[i] = d * mu; wb[i] = m * mu * binv[i];
+  }
+}
+void launch_cg_weights(const DevMesh& dm, const double* mask, double h1, double h2, double* hd, double* wa, double* wb, cudaStream_t st) {
+  k_cg_weights<<<std::min(cdiv(dm.N1, 256), 148 * 16), 256, 0, st>>>(dm.N1, mask, dm.diagA, dm.diagB, dm.vmult, dm.binvm1, h1, h2, hd, wa, wb); LAUNCH_COUNT();
+}
+// x += alpha p ; r -= alpha w   [skipped when first]; then rtz1 = sum r^2 wa, rbn2 = sum r^2 wb.
+// Finaliser applies Nek cggo's convergence test and sets beta.
 __global__ void __launch_bounds__(256)
 k_cg_update_reduce(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ w,
-                   const double* __restrict__ mask, const double* __restrict__ diagA, const double* __restrict__ diagB,
-                   const double* __restrict__ mult, const double* __restrict__ binv, double h1, double h2, double vol, size_t n,
+                   const double* __restrict__ wa, const double* __restrict__ wb, double vol, size_t n,
                    SolverScal* sc, Reducer red, int first, int defer) {
   if (sc->done) return;
   const double alpha = first ? 0.0 : sc->alpha;
@@ -663,25 +678,25 @@ k_cg_update_reduce(double* __restrict__ x, double* __restrict__ r, const double*
     double ri = r[i];
     if (!first) {
       x[i] += alpha * p[i];
-      ri -= alpha * mask[i] * w[i];
+      ri -= alpha * w[i];
       r[i] = ri;
     }
-    double z = ri / (h1 * diagA[i] + h2 * diagB[i]);
-    double m = mult[i];
-    v[0] += ri * z * m;
-    v[1] += ri * ri * m * binv[i];
+    const double r2 = ri * ri;
+    v[0] += r2 * wa[i];
+    v[1] += r2 * wb[i];
     NLK_STREAM4_END
   if (grid_reduce<2>(v, red)) {
     sc->red[0] = v[0]; sc->red[1] = v[1];
     if (!defer) cg_finalize_zr(sc, vol);
   }
 }
-void launch_cg_update_reduce(const DevMesh& dm, double* x, double* r, const double* p, const double* w, const double* mask, double h1,
-                             double h2, SolverScal* sc, Reducer red, int first, int defer, cudaStream_t st) {
+void launch_cg_update_reduce(const DevMesh& dm, double* x, double* r, const double* p, const double* w, const double* wa, const double* wb,
+                             SolverScal* sc, Reducer red, int first, int defer, cudaStream_t st) {
   int grid = stream_grid(dm.N1, RED_BLOCKS);
-  k_cg_update_reduce<<<grid, RED_THREADS, 0, st>>>(x, r, p, w, mask, dm.diagA, dm.diagB, dm.vmult, dm.binvm1, h1, h2, dm.volvm1, dm.N1, sc, red, first, defer);
+  k_cg_update_reduce<<<grid, RED_THREADS, 0, st>>>(x, r, p, w, wa, wb, dm.volvm1, dm.N1, sc, red, first, defer);
   LAUNCH_COUNT();
 }
+
 // ------------------------------------------------------------------------------------------------ dots
 template <int NP, bool W>
 __global__ void __launch_bounds__(256)

@@ -203,13 +203,23 @@ int apply_precond(nlk_ctx* c, const double* r, double* z, const double* in_mul) 
 int helmholtz_solve(nlk_ctx* c, double* rhs, double h1, double h2, const double* mask, double tol, double* x, int* iters) {
   const DevMesh& dm = c->dm;
   const bool multi = c->nccl.nranks > 1;
+  // weights of this (mask, h1, h2): rebuilt only when the Helmholtz coefficients change (the BDF order ramp of each matvec)
+  int slot = -1;
+  for (int k = 0; k < 4; ++k) if (mask == dm.mask[k]) slot = k;
+  if (slot < 0) { set_error("helmholtz_solve: mask is not one of the mesh masks"); return 1; }
+  if (!c->cg_hd[slot]) { if (dev_alloc(c, &c->cg_hd[slot], dm.N1) || dev_alloc(c, &c->cg_wa[slot], dm.N1) || dev_alloc(c, &c->cg_wb[slot], dm.N1)) return 1; c->cg_key_h1[slot] = c->cg_key_h2[slot] = -1.0; }
+  if (c->cg_key_h1[slot] != h1 || c->cg_key_h2[slot] != h2) {
+    launch_cg_weights(dm, mask, h1, h2, c->cg_hd[slot], c->cg_wa[slot], c->cg_wb[slot], c->st);
+    c->cg_key_h1[slot] = h1; c->cg_key_h2[slot] = h2;
+  }
+  const double* hd = c->cg_hd[slot]; const double* wa = c->cg_wa[slot]; const double* wb = c->cg_wb[slot];
   if (ctx_gs(c, Ptr3{{rhs, nullptr, nullptr}}, 1)) return 1;
   launch_lin(c->cg_r, dm.N1, 1.0, rhs, 0, nullptr, 0, nullptr, 0, nullptr, mask, c->st);
   launch_fill(x, dm.N1, 0.0, c->st);
   launch_fill(c->cg_p, dm.N1, 0.0, c->st);
   launch_cg_init(dm, c->d_sc, tol, c->prm.cg_maxit, c->st);
   auto reduce_zr = [&](int first) -> int {
-    launch_cg_update_reduce(dm, x, c->cg_r, c->cg_p, c->cg_w, mask, h1, h2, c->d_sc, c->red, first, multi ? 1 : 0, c->st);
+    launch_cg_update_reduce(dm, x, c->cg_r, c->cg_p, c->cg_w, wa, wb, c->d_sc, c->red, first, multi ? 1 : 0, c->st);
     if (multi) { if (ctx_allreduce(c, c->d_sc->red, 2, false)) return 1; launch_cg_finalize(c->d_sc, 0, dm.volvm1, c->st); }
     return 0;
   };
@@ -218,7 +228,7 @@ int helmholtz_solve(nlk_ctx* c, double* rhs, double h1, double h2, const double*
   int done = 0, it = 0;
   while (!done) {
     for (int b = 0; b < batch; ++b) {
-      launch_axhelm_cg(dm, c->cg_p, c->cg_r, c->cg_w, h1, h2, c->d_sc, c->cg_pap_partial, c->cg_pap_counter, multi ? 1 : 0, c->st);   // w = H p, p.Hp
+      launch_axhelm_cg(dm, c->cg_p, c->cg_r, c->cg_w, hd, h1, h2, c->d_sc, c->cg_pap_partial, c->cg_pap_counter, multi ? 1 : 0, c->st);   // w = H p, p.Hp
       if (ctx_gs(c, Ptr3{{c->cg_w, nullptr, nullptr}}, 1)) return 1;
       if (multi) { if (ctx_allreduce(c, c->d_sc->red + 2, 1, false)) return 1; launch_cg_finalize(c->d_sc, 1, dm.volvm1, c->st); }
       if (reduce_zr(0)) return 1;
