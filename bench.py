@@ -113,7 +113,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "cylinder", "synth3d"])
-    ap.add_argument("--layers", type=int, default=4, help="synth3d: z-layers per GPU (1996 elements each)")
+    ap.add_argument("--layers", type=int, default=6, help="synth3d: z-layers per GPU (1996 elements each)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="time steps in the CPU-baseline sample")
     ap.add_argument("--spinup", type=int, default=30, help="synth3d: untimed time steps before the timed ones (>= warmup)")
     ap.add_argument("--no-cylinder", action="store_true", help="skip the extra cylinder Re=50 matvec block at N=1")
