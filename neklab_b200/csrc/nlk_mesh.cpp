@@ -113,11 +113,10 @@ int build_mesh(HostMesh& hm, int ndim, int lx1, int lxd, int64_t nelg, int64_t n
     const int ax = FACE_AXIS[f], side = FACE_SIDE[f], sa = sym_axis(s, ax);
     if (sa < 0) continue;
     if (sa >= d) { set_error("symmetry code names an axis outside the mesh dimension"); return 1; }
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, elo = 1e300, ehi = -1e300;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     const int nz = d == 3 ? n : 1;
     for (int k = 0; k < nz; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
       const size_t g = (size_t)e * np1 + ((size_t)k * n + j) * n + i;
-      for (int c = 0; c < d; ++c) { elo = std::min(elo, hm.xyz[c][g]); ehi = std::max(ehi, hm.xyz[c][g]); }
       const int idx = ax == 0 ? i : (ax == 1 ? j : k);
       if (idx != (side ? n - 1 : 0)) continue;
       for (int c = 0; c < d; ++c) { lo[c] = std::min(lo[c], hm.xyz[c][g]); hi[c] = std::max(hi[c], hm.xyz[c][g]); }
@@ -128,7 +127,6 @@ int build_mesh(HostMesh& hm, int ndim, int lx1, int lxd, int64_t nelg, int64_t n
                 "boundary codes (neklab_b200.api.resolve_sym) -- plain 'SYM' means the element's own reference axis");
       return 1;
     }
-    (void)elo; (void)ehi;
   }
 
   // ---- geometry
