@@ -12,31 +12,7 @@ from oracle.mesh import coords_from_corners
 pytestmark = pytest.mark.gpu
 
 
-def cheb(N):
-    x = np.cos(np.pi * np.arange(N + 1) / N)
-    c = np.hstack([2.0, np.ones(N - 1), 2.0]) * (-1.0) ** np.arange(N + 1)
-    X = np.tile(x, (N + 1, 1)).T
-    dX = X - X.T
-    D = np.outer(c, 1.0 / c) / (dX + np.eye(N + 1))
-    D -= np.diag(D.sum(axis=1))
-    return D, x
-
-
-def orr_sommerfeld_leading(R, N=120):
-    """Trefethen, Spectral Methods in MATLAB, p. 40 (alpha = 1): eigenvalues lambda of exp(lambda t)."""
-    import scipy.linalg as sla
-    D, x = cheb(N)
-    D2 = (D @ D)[1:N, 1:N]
-    S = np.diag(np.hstack([0.0, 1.0 / (1.0 - x[1:N] ** 2), 0.0]))
-    D4 = (np.diag(1 - x ** 2) @ np.linalg.matrix_power(D, 4) - 8 * np.diag(x) @ np.linalg.matrix_power(D, 3) - 12 * D @ D) @ S
-    D4 = D4[1:N, 1:N]
-    I = np.eye(N - 1)
-    A = (D4 - 2 * D2 + I) / R - 2j * I - 1j * np.diag(1 - x[1:N] ** 2) @ (D2 - I)
-    B = D2 - I
-    ee = sla.eigvals(A, B)
-    ee = ee[np.isfinite(ee)]
-    return ee[np.argmax(ee.real)]
-
+from tests.util import orr_sommerfeld_leading  # noqa: E402  (independent Chebyshev collocation solve)
 
 import os
 
@@ -93,3 +69,31 @@ def test_rayleigh_benard_onset(nlk_lib, Ra, sign):
     assert r["info"] == 0
     assert abs(lam.imag) < 1e-6                               # exchange of stabilities: real leading eigenvalue
     assert np.sign(lam.real) == sign, lam
+
+
+def test_poiseuille_reference_mesh_golden_apply(nlk_lib):
+    """Config C1 on the reference's own mesh (tests/golden/poiseuille_case.npz, x-periodic, wall-graded, Re = 7500, bdf2):
+    one GPU apply of the recorded Ritz vector's real and imaginary parts must reproduce the oracle's stored images
+    (tests/golden/poiseuille_eigvec.npz) and, through them, the growth of the Tollmien-Schlichting wave that
+    tests/test_oracle_poiseuille.py ties to Orr-Sommerfeld."""
+    import json
+    from neklab_b200 import api
+    from tests.test_oracle_poiseuille import load_pair, rayleigh_quotient
+    from tests.util import GOLDEN, nlk_mesh, poiseuille_case
+    om, bf, prm, _ = poiseuille_case()
+    rec = json.load(open(os.path.join(GOLDEN, "poiseuille_eig_oracle.json")))
+    ctx = api.Context(nlk_mesh(om), api.default_params(viscosity=1.0 / 7500.0, torder=2, vtol=1e-12, ptol=1e-12, gmres_maxit=3000, cg_maxit=3000, pr_proj=20))
+    bd = ctx.vec(); bd.upload(bf.v, bf.pr)
+    A = api.exptA_linop(ctx, 1.0, bd)
+    assert A.init()["nsteps"] == rec["nsteps"] == 50
+    ins, gold = load_pair(om)
+    outs = []
+    for v in ins:
+        d = ctx.vec(); d.upload(v.v, v.pr)
+        outs.append(A.matvec(d).download()[0])
+    ctx.close()
+    nrm = lambda f: np.sqrt(sum(float((a * a * om.bm1).sum()) for a in f))
+    for o, g in zip(outs, gold):
+        assert nrm([o[c] - g[c] for c in range(2)]) < 1e-9 * nrm(g)            # iterative (1e-12) vs sparse-direct inner solves
+    mu = complex(rec["mu_re"], rec["mu_im"])
+    assert abs(rayleigh_quotient(om, ins[0].v, ins[1].v, outs[0], outs[1]) - mu) < 2e-3

@@ -83,3 +83,45 @@ def smooth_fields(om: SEMesh, k, seed=0):
 
 def rel(a, b):
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+def poiseuille_case(n=8, lxd=12):
+    """examples/poiseuille/stability/direct_alpha_1 (config C1): the reference's 10 x 12 wall-graded channel mesh
+    (`poiseuille.re2` corners scaled by pi in x as `poiseuille.usr` usrdat does, `.ma2` vertex ids, x-periodic), U = 1 - y^2,
+    Re = 7500 (`viscosity = -7500`), bdf2, tau = 1."""
+    from oracle.mesh import coords_from_corners
+    z = np.load(os.path.join(GOLDEN, "poiseuille_case.npz"))
+    c = z["corners"].copy(); c[:, 0] *= np.pi
+    coords = coords_from_corners(c, n)
+    om = SEMesh(coords, z["vertex"], z["cbc"], lxd)
+    bf = NekVec(om, 2)
+    bf.v = [1.0 - coords[:, 1] ** 2, np.zeros_like(coords[:, 1])]
+    prm = StepParams(viscosity=1.0 / 7500.0, torder=2, vtol=1e-10, ptol=1e-10)
+    return om, bf, prm, z
+
+
+def cheb(N):
+    x = np.cos(np.pi * np.arange(N + 1) / N)
+    c = np.hstack([2.0, np.ones(N - 1), 2.0]) * (-1.0) ** np.arange(N + 1)
+    X = np.tile(x, (N + 1, 1)).T
+    dX = X - X.T
+    D = np.outer(c, 1.0 / c) / (dX + np.eye(N + 1))
+    D -= np.diag(D.sum(axis=1))
+    return D, x
+
+
+def orr_sommerfeld_leading(R, N=120):
+    """Leading temporal eigenvalue lambda (exp(lambda t), alpha = 1) of plane Poiseuille flow by Chebyshev collocation
+    (Trefethen, Spectral Methods in MATLAB, p. 40) -- an anchor independent of the reference and of the oracle."""
+    import scipy.linalg as sla
+    D, x = cheb(N)
+    D2 = (D @ D)[1:N, 1:N]
+    S = np.diag(np.hstack([0.0, 1.0 / (1.0 - x[1:N] ** 2), 0.0]))
+    D4 = (np.diag(1 - x ** 2) @ np.linalg.matrix_power(D, 4) - 8 * np.diag(x) @ np.linalg.matrix_power(D, 3) - 12 * D @ D) @ S
+    D4 = D4[1:N, 1:N]
+    I = np.eye(N - 1)
+    A = (D4 - 2 * D2 + I) / R - 2j * I - 1j * np.diag(1 - x[1:N] ** 2) @ (D2 - I)
+    B = D2 - I
+    ee = sla.eigvals(A, B)
+    ee = ee[np.isfinite(ee)]
+    return ee[np.argmax(ee.real)]
