@@ -81,8 +81,10 @@ def cylinder_inputs():
     return dict(coords=z["coords"], vertex=z["vertex"], cbc=z["cbc"], vel=z["vel"], pr=z["pr"], pid=z["pid"])
 
 
-def extrude(case, n, layers_total, lz_per_layer=0.5):
-    """Extrude the 2-D cylinder mesh (bilinear re-interpolation to lx1=n) into `layers_total` periodic z-layers."""
+def extrude(case, n, layers_total, lz_per_layer=0.5, layer_range=None):
+    """Extrude the 2-D cylinder mesh (bilinear re-interpolation to lx1=n) into `layers_total` periodic z-layers.
+    Connectivity (vertex ids, boundary codes) is always global; with layer_range = (l0, l1) the coordinates and the base flow
+    are generated for those layers only (what one rank of a z-slab partition owns), in the same element order."""
     from neklab_b200.boxmesh import gll_points, lagrange_interp      # host-side input generation (no oracle on this path)
     c2 = case["coords"]; E2 = c2.shape[0]; n0 = c2.shape[-1]
     z0 = gll_points(n0); z1 = gll_points(n)
@@ -90,19 +92,22 @@ def extrude(case, n, layers_total, lz_per_layer=0.5):
     up = lambda a: np.einsum("qj,pi,e...ji->e...qp", I, I, a)
     xy = up(c2[:, :, 0]); vel = up(case["vel"][:, :, 0])
     L = layers_total
-    coords = np.zeros((E2 * L, 3, n, n, n)); U = np.zeros((E2 * L, 3, n, n, n))
+    l0, l1 = (0, L) if layer_range is None else layer_range
+    coords = np.zeros((E2 * (l1 - l0), 3, n, n, n)); U = np.zeros((E2 * (l1 - l0), 3, n, n, n))
     zz = 0.5 * (z1 + 1.0) * lz_per_layer
     nv2 = int(case["vertex"].max())
     vertex = np.zeros((E2 * L, 8), dtype=np.int64)
     cbc = np.full((E2 * L, 6), "E  ", dtype="U3")
     for l in range(L):
         sl = slice(l * E2, (l + 1) * E2)
-        coords[sl, 0] = xy[:, 0][:, None]; coords[sl, 1] = xy[:, 1][:, None]
-        coords[sl, 2] = (l * lz_per_layer + zz)[None, :, None, None]
-        U[sl, 0] = vel[:, 0][:, None]; U[sl, 1] = vel[:, 1][:, None]
         vertex[sl, :4] = case["vertex"] + l * nv2
         vertex[sl, 4:] = case["vertex"] + ((l + 1) % L) * nv2
         cbc[sl, :4] = case["cbc"]; cbc[sl, 4:] = "P  "
+        if l0 <= l < l1:
+            sl = slice((l - l0) * E2, (l - l0 + 1) * E2)
+            coords[sl, 0] = xy[:, 0][:, None]; coords[sl, 1] = xy[:, 1][:, None]
+            coords[sl, 2] = (l * lz_per_layer + zz)[None, :, None, None]
+            U[sl, 0] = vel[:, 0][:, None]; U[sl, 1] = vel[:, 1][:, None]
     return coords, U, vertex, cbc
 
 
@@ -245,11 +250,12 @@ def native_arm(workload, steps, warmup, a, rank, world, local):
     else:
         # synthetic 3-D extruded cylinder, weak scaling: `layers` z-layers (1996 elements each) per GPU, z-slab partition
         L = a.layers * world
-        coords, Uall, vertex, cbc = extrude(case, 8, L)
+        # global connectivity, local coordinates / base flow: this rank owns layers [rank*layers, (rank+1)*layers)
+        coords, Uall, vertex, cbc = extrude(case, 8, L, layer_range=(rank * a.layers, (rank + 1) * a.layers))
         E2 = case["coords"].shape[0]
         gllnid = (np.arange(E2 * L) // (E2 * a.layers)).astype(np.int32) if world > 1 else None
-        sel = slice(None) if gllnid is None else np.where(gllnid == rank)[0]
-        mesh = api.Mesh(coords[sel], vertex, cbc, 12, gllnid=gllnid, rank=rank, nranks=world)
+        sel = slice(None)
+        mesh = api.Mesh(coords, vertex, cbc, 12, gllnid=gllnid, rank=rank, nranks=world)
         prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7, pr_proj=20, coarse_iters=a.coarse_iters)
         nccl_id = None
         if world > 1:
