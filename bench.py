@@ -118,6 +118,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "cylinder", "synth3d"])
+    ap.add_argument("--eigs", action="store_true", help="cylinder block: also time the Krylov-Schur run to the leading eigenpair (kdim 128, nev 2; ~25 s)")
     ap.add_argument("--layers", type=int, default=6, help="synth3d: z-layers per GPU (1996 elements each)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="time steps in the CPU-baseline sample")
     ap.add_argument("--spinup", type=int, default=30, help="synth3d: untimed time steps before the timed ones (>= warmup)")
@@ -181,7 +182,7 @@ def reference_arm(workload, steps, warmup, a):
 
 
 # ----------------------------------------------------------------------------------------------- native arm
-def _cylinder_block(api, case, steps, warmup, device):
+def _cylinder_block(api, case, steps, warmup, device, do_eigs=False):
     """Cylinder Re=50 exptA matvec on ONE GPU (the reference's own config): device-timed and end-to-end matvec/s."""
     mesh = api.Mesh(case["coords"], case["vertex"], case["cbc"], 9)
     prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7, pr_proj=20)   # 1cyl.par: residualProj = yes (mxprev 20)
@@ -212,6 +213,16 @@ def _cylinder_block(api, case, steps, warmup, device):
            "axhelm_us": ms_ax * 1e3, "axhelm_GBps_L2_resident": by_ax / (ms_ax * 1e-3) / 1e9,
            "config": {"elements": int(case["coords"].shape[0]), "lx1": 6, "lxd": 9, "timestepper": "bdf3", "tau": 1.0, "residualProj": 20,
                       "note": "71 856 points (0.57 MB per field): L2-resident, launch/latency-bound by construction"}}
+    # BASELINE metric 3, opt-in (--eigs, ~25 s): wall time of the Krylov-Schur run to nev = 2 converged eigenvalues, kdim = 128
+    out["time_to_leading_eigs_s"] = None
+    out["time_to_leading_eigs_note"] = "not run (pass --eigs); round-1 measurement 24.8 s: profiles/r01_cylinder_eigs_run/"
+    if do_eigs:
+        t0 = time.perf_counter()
+        r = api.linear_stability_analysis_fixed_point(A, 128, 2)
+        ctx.sync()
+        out["time_to_leading_eigs_s"] = time.perf_counter() - t0
+        out["time_to_leading_eigs_note"] = "LightKrylov eigs semantics (Krylov-Schur, kdim 128, nev 2, default tolerance), device-resident basis"
+        out["eigs"] = {"modulus": [float(abs(v)) for v in r["lam"]], "resid": [float(v) for v in r["resid"]], "niter": int(r["niter"]), "info": int(r["info"])}
     ctx.close()
     return out
 
@@ -236,7 +247,7 @@ def native_arm(workload, steps, warmup, a, rank, world, local):
         if world > 1:
             raise SystemExit("the cylinder workload is a single-GPU config (71 856 points); use --workload synth3d for N > 1")
         sampler.start()
-        cyl = _cylinder_block(api, case, steps, warmup, local)
+        cyl = _cylinder_block(api, case, steps, warmup, local, a.eigs)
         clocks = sampler.stop()
         ms_step = cyl["ms_per_matvec"]; value = cyl["matvec_per_s"]; unit = "matvec/s"; metric = "exptA matvec/s"
         e2e = {"value": cyl["e2e_matvec_per_s"], "unit": unit, "h2d_bytes_per_step": cyl["h2d_bytes"], "d2h_bytes_per_step": cyl["d2h_bytes"]}
@@ -318,7 +329,7 @@ def native_arm(workload, steps, warmup, a, rank, world, local):
         ctx.close()
         scaling = "weak"
         if world == 1 and not a.no_cylinder:
-            extra["cylinder_re50"] = _cylinder_block(api, case, 3, 3, local)
+            extra["cylinder_re50"] = _cylinder_block(api, case, 3, 3, local, a.eigs)
     out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
