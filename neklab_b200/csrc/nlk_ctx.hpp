@@ -156,6 +156,10 @@ int step_setup(nlk_ctx* c, double tau, bool transpose);
 int step_setup_cfl(nlk_ctx* c, double tau, double cfl_limit, CPtr3 u);
 int step_advance(nlk_ctx* c, int istep);
 int helmholtz_solve(nlk_ctx* c, double* rhs_local, double h1, double h2, const double* mask, double tol, double* x, int* iters);
+int cg_weights(nlk_ctx* c, const double* mask, double h1, double h2, int* slot_out);
+// opt-in three-field lockstep PCG (nlk_cg3.cu; NLK_CG3=1)
+bool cg3_enabled();
+int helmholtz_solve3(nlk_ctx* c, int nf, double* const* rhs, double h1, double h2, const double* const* masks, double tol, double* const* sol);
 int helmholtz_solve_multi(nlk_ctx* c, int nf, double* const* rhs_local, double h1, double h2, const double* const* masks, double tol, double* const* sol);
 int sync_cg_counter(nlk_ctx* c);
 int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* iters);

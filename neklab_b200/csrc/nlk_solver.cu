@@ -200,10 +200,10 @@ int apply_precond(nlk_ctx* c, const double* r, double* z, const double* in_mul) 
 }
 
 // ------------------------------------------------------------------------------------------------ Helmholtz PCG (hmholtz + cggo)
-int helmholtz_solve(nlk_ctx* c, double* rhs, double h1, double h2, const double* mask, double tol, double* x, int* iters) {
+// weights of (mask, h1, h2) for the streamed PCG: rebuilt only when the Helmholtz coefficients change (the BDF order ramp of
+// each matvec); one slot per mesh mask (velocity components 0..2, temperature 3)
+int cg_weights(nlk_ctx* c, const double* mask, double h1, double h2, int* slot_out) {
   const DevMesh& dm = c->dm;
-  const bool multi = c->nccl.nranks > 1;
-  // weights of this (mask, h1, h2): rebuilt only when the Helmholtz coefficients change (the BDF order ramp of each matvec)
   int slot = -1;
   for (int k = 0; k < 4; ++k) if (mask == dm.mask[k]) slot = k;
   if (slot < 0) { set_error("helmholtz_solve: mask is not one of the mesh masks"); return 1; }
@@ -212,6 +212,14 @@ int helmholtz_solve(nlk_ctx* c, double* rhs, double h1, double h2, const double*
     launch_cg_weights(dm, mask, h1, h2, c->cg_hd[slot], c->cg_wa[slot], c->cg_wb[slot], c->st);
     c->cg_key_h1[slot] = h1; c->cg_key_h2[slot] = h2;
   }
+  *slot_out = slot;
+  return 0;
+}
+int helmholtz_solve(nlk_ctx* c, double* rhs, double h1, double h2, const double* mask, double tol, double* x, int* iters) {
+  const DevMesh& dm = c->dm;
+  const bool multi = c->nccl.nranks > 1;
+  int slot = -1;
+  if (cg_weights(c, mask, h1, h2, &slot)) return 1;
   const double* hd = c->cg_hd[slot]; const double* wa = c->cg_wa[slot]; const double* wb = c->cg_wb[slot];
   if (ctx_gs(c, Ptr3{{rhs, nullptr, nullptr}}, 1)) return 1;
   launch_lin(c->cg_r, dm.N1, 1.0, rhs, 0, nullptr, 0, nullptr, 0, nullptr, mask, c->st);
@@ -256,6 +264,7 @@ int helmholtz_solve_multi(nlk_ctx* c, int nf, double* const* rhs, double h1, dou
     if (launch_cg_persistent(dm, a, c->st)) return 0;
     c->use_cgp = false;                       // cooperative launch unavailable: fall back for good
   }
+  if (cg3_enabled() && nf > 1 && c->nccl.nranks <= 1) return helmholtz_solve3(c, nf, rhs, h1, h2, masks, tol, sol);   // opt-in prototype (nlk_cg3.cu)
   for (int k = 0; k < nf; ++k) {
     if (helmholtz_solve(c, rhs[k], h1, h2, masks[k], tol, c->cg_x, nullptr)) return 1;
     launch_lin(sol[k], dm.N1, 1.0, sol[k], 1.0, c->cg_x, 0, nullptr, 0, nullptr, nullptr, c->st);
