@@ -302,6 +302,7 @@ int nlk_ctx_destroy(nlk_ctx* c) {
     for (cudaEvent_t e : c->ph.pool) cudaEventDestroy(e);
   }
   if (c->crs_graph) cudaGraphExecDestroy(c->crs_graph);
+  cg3_release(c);
   for (void* p : c->allocs) cudaFree(p);
   if (c->h_sc) cudaFreeHost(c->h_sc);
   if (c->h_red) cudaFreeHost(c->h_red);

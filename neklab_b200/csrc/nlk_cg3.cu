@@ -222,14 +222,19 @@ static void axhelm3_dispatch(const DevMesh& dm, const Cg3& a, double h1, double 
   ++g_launches;
 }
 
-struct Cg3State {          // lazily allocated per context (kept in a side table so that nlk_ctx stays untouched)
-  nlk_ctx* owner = nullptr;
+struct Cg3State {          // lazily allocated, owned by the context (nlk_ctx::cg3, released by cg3_release at destruction)
   double* x[3] = {nullptr, nullptr, nullptr}; double* p[3] = {nullptr, nullptr, nullptr}; double* w[3] = {nullptr, nullptr, nullptr};
   SolverScal* d_sc = nullptr; SolverScal* h_sc = nullptr;
   double* pap_partial = nullptr; double* upd_partial = nullptr; unsigned int* counters = nullptr;
   int upd_grid = 0;
 };
-static Cg3State g_cg3;
+void cg3_release(nlk_ctx* c) {
+  auto* S = static_cast<Cg3State*>(c->cg3);
+  if (!S) return;
+  if (S->h_sc) cudaFreeHost(S->h_sc);
+  delete S;                                            // (device buffers are in c->allocs)
+  c->cg3 = nullptr;
+}
 
 bool cg3_enabled() { static const bool on = getenv("NLK_CG3") != nullptr; return on; }
 
@@ -237,14 +242,15 @@ bool cg3_enabled() { static const bool on = getenv("NLK_CG3") != nullptr; return
 int helmholtz_solve3(nlk_ctx* c, int nf, double* const* rhs, double h1, double h2, const double* const* masks, double tol, double* const* sol) {
   const DevMesh& dm = c->dm;
   if (nf < 1 || nf > 3 || c->nccl.nranks > 1) { set_error("helmholtz_solve3: 1..3 fields, single rank"); return 1; }
-  Cg3State& S = g_cg3;
-  if (S.owner != c) {                                  // (one context per process, like the reference; buffers follow the context)
-    S = Cg3State{}; S.owner = c;
-    for (int k = 0; k < 3; ++k) if (dev_alloc(c, &S.x[k], dm.N1) || dev_alloc(c, &S.p[k], dm.N1) || dev_alloc(c, &S.w[k], dm.N1)) return 1;
-    S.upd_grid = (int)std::min<size_t>((dm.N1 + 255) / 256, 1184);
-    if (dev_alloc(c, &S.d_sc, 3) || dev_alloc(c, &S.pap_partial, 3 * ((size_t)dm.E + 1)) || dev_alloc(c, &S.upd_partial, (size_t)6 * S.upd_grid) || dev_alloc(c, &S.counters, 4)) return 1;
-    NLK_CUDA(cudaMallocHost((void**)&S.h_sc, 3 * sizeof(SolverScal)));       // (released with the process)
+  if (!c->cg3) {
+    auto* N = new Cg3State{};
+    c->cg3 = N;
+    for (int k = 0; k < 3; ++k) if (dev_alloc(c, &N->x[k], dm.N1) || dev_alloc(c, &N->p[k], dm.N1) || dev_alloc(c, &N->w[k], dm.N1)) return 1;
+    N->upd_grid = (int)std::min<size_t>((dm.N1 + 255) / 256, 1184);
+    if (dev_alloc(c, &N->d_sc, 3) || dev_alloc(c, &N->pap_partial, 3 * ((size_t)dm.E + 1)) || dev_alloc(c, &N->upd_partial, (size_t)6 * N->upd_grid) || dev_alloc(c, &N->counters, 4)) return 1;
+    NLK_CUDA(cudaMallocHost((void**)&N->h_sc, 3 * sizeof(SolverScal)));
   }
+  Cg3State& S = *static_cast<Cg3State*>(c->cg3);
   if (c3_D_n != dm.n) { NLK_CUDA(cudaMemcpyToSymbolAsync(c3_D, dm.D, sizeof(double) * dm.n * dm.n, 0, cudaMemcpyDeviceToDevice, c->st)); c3_D_n = dm.n; }
   Cg3 a{}; a.nf = nf;
   for (int k = 0; k < nf; ++k) {
