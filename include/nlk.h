@@ -101,6 +101,11 @@ typedef struct {
                               1 = consistent combination of the rst fields; 2 = matvec ignores input rst fields.
                               1/2 are NOT the reference behaviour; they exist to document its effect */
   int32_t coarse_iters;    /* Jacobi-PCG iterations of the sparse coarse solve used above 5000 vertices (crs_solve analogue) */
+  int32_t step_variant;    /* 0 (default). Bit field of documented deviations in the start-up / pressure bookkeeping of the step,
+                              used ONLY by the golden-value sweep of DESIGN.md 1.1 (tests/test_gpu_golden_sweep.py):
+                              1 = prlagp is never updated (stays 0), 2 = dp is added to prp instead of to the extrapolated p*,
+                              4 = the pressure of vec_in is ignored (prp = 0 at the start of every matvec),
+                              8 = first-order pressure extrapolation on every step (p* = p^n) */
 } nlk_params;
 
 int nlk_params_default(nlk_params* p);

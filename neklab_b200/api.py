@@ -40,7 +40,7 @@ class Params(C.Structure):
                 ("ptol", C.c_double), ("ifheat", C.c_int32), ("conductivity", C.c_double), ("rhocp", C.c_double),
                 ("ttol", C.c_double), ("buoyancy", C.c_double * 3), ("filter_weight", C.c_double),
                 ("filter_cutoff", C.c_double), ("cg_maxit", C.c_int32), ("gmres_maxit", C.c_int32), ("lgmres", C.c_int32),
-                ("precond", C.c_int32), ("pr_proj", C.c_int32), ("cfl_limit", C.c_double), ("rst_mode", C.c_int32), ("coarse_iters", C.c_int32)]
+                ("precond", C.c_int32), ("pr_proj", C.c_int32), ("cfl_limit", C.c_double), ("rst_mode", C.c_int32), ("coarse_iters", C.c_int32), ("step_variant", C.c_int32)]
 
 
 class Stats(C.Structure):

@@ -550,6 +550,7 @@ int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose) {
   if (push_baseflow(op)) return 1;
   if (step_setup(c, op->tau, transpose)) return 1;
   if (state_from_vec(c, in->v, in->pr, in->theta)) return 1;
+  if (c->prm.step_variant & 4) NLK_CUDA(cudaMemsetAsync(c->prp, 0, c->dm.N2 * sizeof(double), c->st));
   if (reset_history_pub(c)) return 1;
   for (int istep = 1; istep <= c->nsteps; ++istep) {
     if (step_advance(c, istep)) return 1;

@@ -109,7 +109,7 @@ void launch_opdiv_fused(const DevMesh& dm, CPtr3 u, double* p, double scale, con
 void launch_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st);
 // K3/K4 convection (convect.f convect_new / convect_adj): out_f (+)= alpha * J^T W[(J C . rx) . grad J u_f]
 void launch_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double alpha, int accumulate, cudaStream_t st);
-void launch_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st);
+void launch_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st, int nj = -1);   // nj pairs (c_j, U_j) summed (default ndim)
 // K7  fused rhs tail: makextp + makebdfp + lagfieldp for ncomp fields
 struct RhsTail { double* bf[4]; double* e1[4]; double* e2[4]; const double* u[4]; double* lag1[4]; double* lag2[4]; double coef[4]; };
 void launch_rhs_tail(const DevMesh& dm, const RhsTail& t, int nf, double ab0, double ab1, double ab2, double bd1, double bd2, double bd3,
@@ -158,7 +158,7 @@ bool tp_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, const double*
 bool tp_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st);
 bool tp_schwarz_fdm(const DevMesh& dm, const double* w, double* z, double* t, cudaStream_t st);
 bool tp_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double alpha, int accumulate, cudaStream_t st);
-bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st);
+bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st, int nj);
 extern thread_local long g_launches;   // counts kernel launches issued through these wrappers
 
 }  // namespace nlk

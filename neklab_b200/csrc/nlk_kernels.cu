@@ -552,7 +552,7 @@ void launch_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, doubl
 // out_i (+)= alpha * I^T [ sum_j (I c_j) * sum_k rxd[k][i] D_k (I U_j) ]   -- Nek convect_adj
 __global__ void k_convect_adj(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __restrict__ rxd, const double* __restrict__ I1dg,
                               const double* __restrict__ I1dtg, const double* __restrict__ Ddg, int n, int m, int d, double alpha,
-                              int accumulate) {
+                              int accumulate, int nj) {
   extern __shared__ double sm[];
   const int nz = d == 3 ? n : 1, mz = d == 3 ? m : 1;
   const int np1 = n * n * nz, npd = m * m * mz;
@@ -564,7 +564,7 @@ __global__ void k_convect_adj(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __restr
   for (int i = threadIdx.x; i < d * npd; i += blockDim.x) AC[i] = 0.0;
   __syncthreads();
   const double* rx = rxd + e * (size_t)(d * d) * npd;
-  for (int j = 0; j < d; ++j) {
+  for (int j = 0; j < nj; ++j) {
     // CF = I c_j ; UF = I U_j
     for (int pass = 0; pass < 2; ++pass) {
       const double* src = (pass == 0 ? cf.p[j] : U.p[j]) + e * np1;
@@ -591,12 +591,13 @@ __global__ void k_convect_adj(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __restr
     __syncthreads();
   }
 }
-void launch_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st) {
-  if (tp_convect_adj(dm, U, c, out, alpha, accumulate, st)) return;
+void launch_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st, int nj) {
+  if (nj < 0) nj = dm.ndim;
+  if (tp_convect_adj(dm, U, c, out, alpha, accumulate, st, nj)) return;
   size_t smem = (size_t)(2 * dm.m * dm.n + dm.m * dm.m + 7 * dm.npd) * sizeof(double);
   static size_t set = 0;
   if (smem > 48 * 1024 && smem > set) { cudaFuncSetAttribute(k_convect_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
-  k_convect_adj<<<(unsigned)dm.E, elem_threads(dm.npd), smem, st>>>(U, c, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, dm.n, dm.m, dm.ndim, alpha, accumulate);
+  k_convect_adj<<<(unsigned)dm.E, elem_threads(dm.npd), smem, st>>>(U, c, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, dm.n, dm.m, dm.ndim, alpha, accumulate, nj);
   LAUNCH_COUNT();
 }
 

@@ -496,7 +496,7 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
 // ------------------------------------------------------------------------------------------------ K4 convect_adj
 template <int N, int MD, int DIM>
 __global__ void k_convect_adj_t(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __restrict__ rxd, const double* __restrict__ I1dg,
-                                const double* __restrict__ I1dtg, const double* __restrict__ Ddg, double alpha, int accumulate) {
+                                const double* __restrict__ I1dtg, const double* __restrict__ Ddg, double alpha, int accumulate, int nj) {
   constexpr int n = N, m = MD, d = DIM, nz = DIM == 3 ? N : 1, mz = DIM == 3 ? MD : 1;
   constexpr int np1 = n * n * nz, npd = m * m * mz;
   constexpr int PN = DIM == 3 ? (n | 1) : n, PM = DIM == 3 ? (m | 1) : m, npdP = PM * m * mz;   // odd x-pitches, see k_convect_t
@@ -509,7 +509,7 @@ __global__ void k_convect_adj_t(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __res
   __syncthreads();
   const double* rx = rxd + e * (size_t)(d * d) * npd;
 #pragma unroll 1
-  for (int j = 0; j < d; ++j) {
+  for (int j = 0; j < nj; ++j) {
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       const double* src = (pass == 0 ? cf.p[j] : U.p[j]) + e * np1;
@@ -678,12 +678,12 @@ bool tp_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double al
 #undef FN
   ++g_launches; return true;
 }
-bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st) {
+bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st, int nj) {
   size_t smem = convect_smem(dm);
   if (smem > 220 * 1024) return false;
   ensure_const_ops(dm, st);
   int thr = tp_threads(dm.m, dm.ndim, dm.npd);
-#define FN(N_, M_, D_) { static bool s_ = false; if (!s_) { set_smem(k_convect_adj_t<N_, M_, D_>, smem); s_ = true; } k_convect_adj_t<N_, M_, D_><<<(unsigned)dm.E, thr, smem, st>>>(U, c, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, alpha, accumulate); }
+#define FN(N_, M_, D_) { static bool s_ = false; if (!s_) { set_smem(k_convect_adj_t<N_, M_, D_>, smem); s_ = true; } k_convect_adj_t<N_, M_, D_><<<(unsigned)dm.E, thr, smem, st>>>(U, c, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, alpha, accumulate, nj); }
   TP_SWITCH_NM((dm.n * 100 + dm.m) * 10 + dm.ndim)
 #undef FN
   ++g_launches; return true;

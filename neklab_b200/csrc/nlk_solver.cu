@@ -459,7 +459,7 @@ int step_advance(nlk_ctx* c, int istep) {
   int ph = c->ph.begin(PH_MAKEF, st);
   // ---- igeom = 1: makefp = makeufp + advabp(_adjoint) + makextp + makebdfp ; lagfieldp
   for (int k = 0; k < d; ++k) {
-    const double* f0 = (P.ifheat && P.buoyancy[k] != 0.0) ? c->tp : nullptr;
+    const double* f0 = (P.ifheat && P.buoyancy[k] != 0.0 && !c->adjoint) ? c->tp : nullptr;      // adjoint: the buoyancy coupling moves to the temperature equation
     const double* f1 = c->has_forcing ? c->forcing[k] : nullptr;
     if (f0 || f1) launch_lin(c->bf[k], dm.N1, P.buoyancy[k], f0, 1.0, f1, 0, nullptr, 0, nullptr, dm.bm1, st);
     else NLK_CUDA(cudaMemsetAsync(c->bf[k], 0, dm.N1 * sizeof(double), st));
@@ -474,17 +474,23 @@ int step_advance(nlk_ctx* c, int istep) {
   } else {
     launch_convect_adj(dm, Ub, up, Ptr3{{c->bf[0], c->bf[1], c->bf[2]}}, -rho, 1, st);            // (grad U)^T u'
     launch_convect(dm, CPtr4{{c->vp[0], c->vp[1], c->vp[2], nullptr}}, d, Ub, bf4, +rho, 1, st);
+    // exptA_temp_linop%rmatvec (exponential_propagator_temp.f90:62-107): - theta' grad(T_base), the transpose of u'.grad T
+    if (P.ifheat) launch_convect_adj(dm, CPtr3{{c->T, nullptr, nullptr}}, CPtr3{{c->tp, nullptr, nullptr}}, Ptr3{{c->bf[0], c->bf[1], c->bf[2]}}, -P.rhocp, 1, st, 1);
   }
   RhsTail t{};
   int nf = d;
   for (int k = 0; k < d; ++k) { t.bf[k] = c->bf[k]; t.e1[k] = c->exx1[k]; t.e2[k] = c->exx2[k]; t.u[k] = c->vp[k]; t.lag1[k] = c->vlag[0][k]; t.lag2[k] = c->vlag[1][k]; t.coef[k] = rho / dt; }
   if (P.ifheat) {
-    if (c->adjoint) { set_error("adjoint Boussinesq step is out of scope (no reference config uses it)"); return 1; }
     if (c->nonlinear) { set_error("nonlinear Boussinesq stepper (nek_system_temp) is out of scope this round"); return 1; }
     NLK_CUDA(cudaMemsetAsync(c->bq, 0, dm.N1 * sizeof(double), st));
     Ptr4 bq4{{c->bq, nullptr, nullptr, nullptr}};
-    launch_convect(dm, CPtr4{{c->T, nullptr, nullptr, nullptr}}, 1, up, bq4, -P.rhocp, 1, st);    // u'.grad T
-    launch_convect(dm, CPtr4{{c->tp, nullptr, nullptr, nullptr}}, 1, Ub, bq4, -P.rhocp, 1, st);   // U.grad T'
+    if (!c->adjoint) {
+      launch_convect(dm, CPtr4{{c->T, nullptr, nullptr, nullptr}}, 1, up, bq4, -P.rhocp, 1, st);    // u'.grad T
+      launch_convect(dm, CPtr4{{c->tp, nullptr, nullptr, nullptr}}, 1, Ub, bq4, -P.rhocp, 1, st);   // U.grad T'
+    } else {                                                                                        // adjoint: + U.grad theta' + buoyancy . u'
+      launch_convect(dm, CPtr4{{c->tp, nullptr, nullptr, nullptr}}, 1, Ub, bq4, +P.rhocp, 1, st);
+      for (int k = 0; k < d; ++k) if (P.buoyancy[k] != 0.0) launch_axpy_mm(c->bq, dm.N1, c->bq, P.buoyancy[k], c->vp[k], dm.bm1, nullptr, st);
+    }
     t.bf[nf] = c->bq; t.e1[nf] = c->vgradt1; t.e2[nf] = c->vgradt2; t.u[nf] = c->tp; t.lag1[nf] = c->tlag[0]; t.lag2[nf] = c->tlag[1]; t.coef[nf] = P.rhocp / dt;
     ++nf;
   }
@@ -495,7 +501,8 @@ int step_advance(nlk_ctx* c, int istep) {
   if (!c->nonlinear)    // bcdirvc: homogeneous for perturbations; the nonlinear state keeps its (inflow) boundary values
     for (int k = 0; k < d; ++k) launch_lin(c->vp[k], dm.N1, 1.0, c->vp[k], 0, nullptr, 0, nullptr, 0, nullptr, dm.mask[k], st);
   double* pext = c->pw[3];
-  if (nbd == 3) launch_lin(pext, dm.N2, 2.0, c->prp, -1.0, c->prlag, 0, nullptr, 0, nullptr, nullptr, st);                    // extrapprp
+  const int variant = P.step_variant;
+  if (nbd == 3 && !(variant & 8)) launch_lin(pext, dm.N2, 2.0, c->prp, -1.0, c->prlag, 0, nullptr, 0, nullptr, nullptr, st);    // extrapprp
   else NLK_CUDA(cudaMemcpyAsync(pext, c->prp, dm.N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
   Ptr3 gp{{c->wk[3], c->wk[4], c->wk[5]}};
   launch_opgradt(dm, pext, gp, st);
@@ -514,8 +521,8 @@ int step_advance(nlk_ctx* c, int istep) {
   double* rhs = c->pw[4];
   launch_opdiv(dm, CPtr3{{c->vp[0], c->vp[1], c->vp[2]}}, rhs, -1.0, st);
   if (ortho(c, rhs)) return 1;
-  NLK_CUDA(cudaMemcpyAsync(c->prlag, c->prp, dm.N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));                            // lagpresp
-  NLK_CUDA(cudaMemcpyAsync(c->prp, pext, dm.N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));                                // up = prextr (+ dp below)
+  if (!(variant & 1)) NLK_CUDA(cudaMemcpyAsync(c->prlag, c->prp, dm.N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));        // lagpresp
+  if (!(variant & 2)) NLK_CUDA(cudaMemcpyAsync(c->prp, pext, dm.N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));            // up = prextr (+ dp below)
   double* xs = c->pw[3];                                                                                                        // pext is dead from here
   c->ph.end(ph, st); ph = c->ph.begin(PH_PRES, st);
   if (pressure_solve_projected(c, rhs, P.ptol, xs, nullptr)) return 1;

@@ -249,16 +249,40 @@ class SchwarzCoarse:
             else:
                 self.shape.append(H[k][:, None, None] * H[j][None, :, None] * H[i][None, None, :])
         self.nv = int(m.vertex.max())
-        A0 = np.zeros((self.nv, self.nv))
-        for v in range(self.nv):
-            e0 = np.zeros(self.nv); e0[v] = 1.0
-            A0[:, v] = self.restrict(ops.cdabdtp(m, self.prolong(e0), self.rho))
+        if self.nv <= 300:                                  # column by column through the operator itself (small cases: cross-check)
+            A0 = np.zeros((self.nv, self.nv))
+            for v in range(self.nv):
+                e0 = np.zeros(self.nv); e0[v] = 1.0
+                A0[:, v] = self.restrict(ops.cdabdtp(m, self.prolong(e0), self.rho))
+        else:
+            A0 = self.galerkin_sparse().toarray()
         A0 = 0.5 * (A0 + A0.T)
         self.A0 = A0
         if m.has_outflow:
             self.A0inv = np.linalg.inv(A0)
         else:
             self.A0inv = np.linalg.pinv(A0, rcond=1e-12, hermitian=True)
+
+    def galerkin_sparse(self):
+        """R0 E R0^T assembled algebraically: E = sum_c D_c W_c D_c^T with W_c = mask_c binvm1 / rho on the unique velocity
+        nodes, so A0 = sum_c M_c^T W_c M_c with M_c = Q^T D_c^T R0^T (the velocity-space image of every vertex hat function,
+        one `cdtp` per corner and component on the whole mesh).  Equal to the column-by-column construction to round-off."""
+        import scipy.sparse as sp
+        m = self.mesh
+        E, nn = m.E, m.bm1[0].size
+        rows = np.asarray(m.gidx).reshape(E, nn)
+        A0 = None
+        for c in range(m.ndim):
+            Mc = None
+            for k in range(2 ** m.ndim):
+                loc = ops.cdtp(m, np.broadcast_to(self.shape[k][None], m.bm2.shape), c).reshape(E, nn)
+                cols = np.repeat((m.vertex[:, k] - 1)[:, None], nn, axis=1)
+                t = sp.csr_matrix((loc.ravel(), (rows.ravel(), cols.ravel())), shape=(m.nglob, self.nv))
+                Mc = t if Mc is None else Mc + t
+            wg = np.zeros(m.nglob); wg[m.gidx] = (m.vmask[c] * m.binvm1).ravel() / self.rho
+            t = (Mc.T @ sp.diags(wg) @ Mc)
+            A0 = t if A0 is None else A0 + t
+        return A0.tocsr()
 
     def prolong(self, c):
         m = self.mesh
