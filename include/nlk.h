@@ -174,6 +174,10 @@ int nlk_exptA_stats(const nlk_op* op, nlk_stats* out);
 /* bench hook: start from `in` (history reset as at the top of exptA_matvec), run nwarm untimed + nsteps timed perturbation
  * time steps (body of the loop at exponential_propagator.f90:39-46) and return the device time of the timed ones */
 int nlk_exptA_time_steps(nlk_op* op, const nlk_vec* in, int32_t nwarm, int32_t nsteps, double* ms_timed);
+/* nek2vec / vec2nek on the DEVICE-resident solver state (src/neklab_utils.f90:84-134): copy the perturbation fields
+ * vxp,vyp,vzp,prp,tp of the context into / out of a vector (intent(out) semantics: nrst of the vector is reset) */
+int nlk_nek2vec(nlk_ctx* c, nlk_vec* out);
+int nlk_vec2nek(nlk_ctx* c, const nlk_vec* in);
 int nlk_exptA_set_baseflow(nlk_op* op, const nlk_vec* baseflow);      /* nek_jacobian%X = X (src/systems/neklab_systems.f90) */
 /* nek_system%response (src/systems/fixed_point.f90:4-40): out = F_tau(in) - in with the NONLINEAR stepper
  * (Nek `fluid`/`plan3`: makef/advab, cresvif, ophinv, incomprn), dt from the CFL of `in` at cfl_limit (0.4 in the reference) */
@@ -212,7 +216,9 @@ int nlk_test_pressure(nlk_ctx* c, const double* rhs, double tol, double* x, int3
 int nlk_test_precond(nlk_ctx* c, const double* r, double* z);                                /* K10/K11 */
 int nlk_test_cfl(nlk_ctx* c, const double* ux, const double* uy, const double* uz, double dt, double* cfl); /* K14 */
 /* time a device-resident kernel nrep times on the ctx stream with CUDA events; returns mean ms per launch.
- * which: 0 axhelm, 1 dssum, 2 cdabdtp, 3 convect(all comps), 4 precond, 5 vec dot, 6 sparse coarse solve, 7 Schwarz branch of the preconditioner */
+ * which: 0 axhelm, 1 dssum, 2 cdabdtp, 3 convect(all comps), 4 precond, 5 vec dot, 6 sparse coarse solve, 7 Schwarz branch of the preconditioner,
+ * 8 the FUSED Helmholtz apply the Jacobi-PCG launches (p = hd r + beta p on load, p.Ap on the way out), 9 the PCG update+reduce kernel,
+ * 10 opgradt alone, 11 opdiv (fused load scaling) alone, 12 dssum of three fields */
 int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_launch, double* algo_bytes);
 
 #ifdef __cplusplus

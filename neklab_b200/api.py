@@ -56,7 +56,7 @@ nlk_mesh_field nlk_mesh_neighbor nlk_mesh_basis nlk_dense_eig nlk_params_default
 nlk_ctx_set_dt nlk_comm_unique_id nlk_ctx_comm_init nlk_ctx_sync nlk_ctx_stream nlk_vec_create nlk_vec_destroy nlk_vec_copy nlk_vec_zero
 nlk_vec_rand nlk_vec_scal nlk_vec_axpby nlk_vec_dot nlk_vec_norm nlk_vec_size nlk_vec_save_rst nlk_vec_get_rst nlk_vec_nrst
 nlk_vec_clear_rst nlk_vec_upload nlk_vec_download nlk_zvec_scal nlk_zvec_axpby nlk_zvec_dot nlk_basis_innerprod nlk_basis_axpy nlk_basis_dgs nlk_exptA_create
-nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_exptA_time_steps nlk_exptA_set_baseflow nlk_nonlinear_map nlk_newton_fixed_point nlk_ctx_set_forcing
+nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_exptA_time_steps nlk_exptA_set_baseflow nlk_nonlinear_map nlk_newton_fixed_point nlk_ctx_set_forcing nlk_nek2vec nlk_vec2nek
 nlk_eigs nlk_svds nlk_gmres nlk_test_axhelm nlk_test_dssum nlk_test_opdiv nlk_test_opgradt nlk_test_cdabdtp nlk_test_convect
 nlk_test_convect_adj nlk_test_helmholtz nlk_test_pressure nlk_test_precond nlk_test_cfl nlk_bench_kernel""".split()
 
@@ -282,6 +282,14 @@ class Context:
     def bench_kernel(self, which, nrep):
         ms = C.c_double(); by = C.c_double()
         _chk(lib().nlk_bench_kernel(self.h, C.c_int32(which), C.c_int32(nrep), C.byref(ms), C.byref(by))); return ms.value, by.value
+
+    def nek2vec(self, vec=None):
+        """`nek2vec` (src/neklab_utils.f90:84-134) on the device-resident state."""
+        vec = vec or nek_dvector(self)
+        _chk(lib().nlk_nek2vec(self.h, vec.h)); return vec
+
+    def vec2nek(self, vec):
+        _chk(lib().nlk_vec2nek(self.h, vec.h))
 
     def set_forcing(self, f):
         f = [_f64(x) for x in f]

@@ -582,6 +582,8 @@ int nlk_exptA_init(nlk_op* op) { if (push_baseflow(op)) return 1; return step_se
 int nlk_exptA_matvec(nlk_op* op, const nlk_vec* in, nlk_vec* out) { return exptA_apply(op, in, out, false); }
 int nlk_exptA_rmatvec(nlk_op* op, const nlk_vec* in, nlk_vec* out) { return exptA_apply(op, in, out, true); }
 int nlk_exptA_set_baseflow(nlk_op* op, const nlk_vec* bf) { return nlk_vec_copy(op->baseflow, bf); }
+int nlk_nek2vec(nlk_ctx* c, nlk_vec* out) { if (copy_fields(c, out->v, out->pr, out->theta, c->vp, c->prp, c->tp)) return 1; out->nrst = 0; return 0; }
+int nlk_vec2nek(nlk_ctx* c, const nlk_vec* in) { return state_from_vec(c, in->v, in->pr, in->theta); }
 
 int nlk_nonlinear_map(nlk_ctx* c, double tau, double cfl_limit, const nlk_vec* in, nlk_vec* out) {
   if (in == out) { set_error("nonlinear_map: vec_in and vec_out must differ"); return 1; }
@@ -760,10 +762,22 @@ int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_lau
               launch_schwarz_embed(dm, c->pw[3], nullptr, c->sw_w, c->st); if (ctx_gs(c, Ptr3{{c->sw_w, nullptr, nullptr}}, 1)) return 1;
               launch_schwarz_fdm(dm, c->sw_w, c->sw_z, c->sw_t, c->st); if (ctx_gs(c, Ptr3{{c->sw_t, nullptr, nullptr}}, 1)) return 1;
               launch_schwarz_gather(dm, c->sw_z, c->sw_t, c->pw[4], c->st); break;
+      case 8: { int slot; if (cg_weights(c, dm.mask[0], 0.02, 180.0, &slot)) return 1;
+                launch_axhelm_cg(dm, c->cg_p, c->cg_r, c->cg_w, c->cg_hd[slot], 0.02, 180.0, c->d_sc, c->cg_pap_partial, c->cg_pap_counter, 1, c->st); break; }
+      case 9: { int slot; if (cg_weights(c, dm.mask[0], 0.02, 180.0, &slot)) return 1;
+                launch_cg_update_reduce(dm, c->cg_x, c->cg_r, c->cg_p, c->cg_w, c->cg_wa[slot], c->cg_wb[slot], c->d_sc, c->red, 0, 1, c->st); break; }
+      case 10: launch_opgradt(dm, c->pw[3], Ptr3{{c->wk[0], c->wk[1], c->wk[2]}}, c->st); break;
+      case 11: launch_opdiv_fused(dm, CPtr3{{c->wk[0], c->wk[1], c->wk[2]}}, c->pw[4], 1.0, dm.binvm1, nullptr, c->st); break;
+      case 12: return ctx_gs(c, Ptr3{{c->wk[0], c->wk[1], c->wk[2]}}, d);
       default: set_error("unknown bench kernel"); return 1;
     }
     return 0;
   };
+  if (which == 8 || which == 9) {      // the PCG kernels read their scalars from the device: fresh state, deferred finalisation (no early exit)
+    launch_cg_init(dm, c->d_sc, 0.0, 1 << 30, c->st);
+    NLK_CUDA(cudaMemcpyAsync(c->cg_r, c->wk[0], dm.N1 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    NLK_CUDA(cudaMemsetAsync(c->cg_p, 0, dm.N1 * sizeof(double), c->st));
+  }
   for (int i = 0; i < 3; ++i) if (run()) return 1;
   cudaEventRecord(e0, c->st);
   for (int i = 0; i < nrep; ++i) if (run()) return 1;
@@ -782,6 +796,11 @@ int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_lau
     case 5: bytes = (d + 1) * 8.0 * N1; break;
     case 6: bytes = (double)c->crs_iters * (12.0 * (double)c->crs_nnz + 9 * 8.0 * (double)dm.nvert); break;   // CSR values + indices per SpMV, vectors
     case 7: bytes = 2 * 8.0 * N2 + 6 * 8.0 * N1; break;
+    case 8: bytes = (5 + dm.ng + 1) * 8.0 * N1; break;                       // r, hd, p in; p, w out; g-factors; bm1
+    case 9: bytes = 8 * 8.0 * N1; break;                                     // x, r, p, w, wa, wb in; x, r out
+    case 10: bytes = d * 8.0 * N1 + (1 + d * d) * 8.0 * N2; break;
+    case 11: bytes = 2.0 * d * 8.0 * N1 + (1 + d * d) * 8.0 * N2; break;     // u_c and binvm1*mask per component in; metrics; p out
+    case 12: bytes = d * (double)c->mesh->hm.gs_idx.size() * 16.0 + (double)c->mesh->hm.gs_idx.size() * 4.0; break;
   }
   if (algo_bytes) *algo_bytes = bytes;
   return 0;

@@ -371,6 +371,22 @@ int build_mesh(HostMesh& hm, int ndim, int lx1, int lxd, int64_t nelg, int64_t n
     s = t;
   }
   hm.nglob_local = ndistinct_surf + E * nint;
+  // Order the shared groups by the local address of their first copy (copies inside a group stay in ascending local order, so
+  // every sum is taken in the same order as before): consecutive threads of k_gs then walk the owner element's surface in
+  // memory order, and the partner copies sit on the neighbours' matching faces -- each 32-byte sector of a face is touched by
+  // one or two adjacent warps instead of by warps scattered over the global-id order (r01 ncu: 6.8x the useful DRAM bytes).
+  {
+    const size_t ng = hm.gs_off.size() - 1;
+    std::vector<int32_t> ord(ng); for (size_t i = 0; i < ng; ++i) ord[i] = (int32_t)i;
+    std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) { return hm.gs_idx[hm.gs_off[x]] < hm.gs_idx[hm.gs_off[y]]; });
+    std::vector<int32_t> noff(1, 0), nidx; nidx.reserve(hm.gs_idx.size()); std::vector<int32_t> nfirst; nfirst.reserve(ng);
+    for (size_t i = 0; i < ng; ++i) {
+      const int32_t g = ord[i];
+      for (int32_t u = hm.gs_off[g]; u < hm.gs_off[g + 1]; ++u) nidx.push_back(hm.gs_idx[u]);
+      noff.push_back((int32_t)nidx.size()); nfirst.push_back(hm.gs_first[g]);
+    }
+    hm.gs_off.swap(noff); hm.gs_idx.swap(nidx); hm.gs_first.swap(nfirst);
+  }
   hm.neigh.clear();
   for (auto& kv : nb_first) {
     Neighbor nb; nb.rank = kv.first;

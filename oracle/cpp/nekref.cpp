@@ -41,6 +41,7 @@ struct Ref {
   // state
   vec U[3], T, vp[3], prp, tp, vlag[2][3], exx1[3], exx2[3], prlag, tlag[2], vg1, vg2, forcing[3]; int has_forcing = 0;
   long cg_iters = 0, gm_iters = 0;
+  int pr_proj = 0; std::vector<vec> projX, projEX;      // pressure residual projection (Nek setrhsp/gensolnp; .par residualProj, SIZE mxprev)
 };
 
 // out[(k,j,i')] = sum_i M[i'][i] in[(k,j,i)] along axis ax (0 = x fastest, 1 = y, 2 = z); dims of `in` are (n0,n1,n2) = (x,y,z)
@@ -399,6 +400,35 @@ static int uzawa_gmres(Ref& R, const double* res, double tol, double* x) {
   R.gm_iters += it; return it;
 }
 
+// Pressure residual projection (Nek `setrhsp`/`gensolnp`): the rhs is projected onto the span of up to pr_proj previous
+// solutions kept E-orthonormal; same restatement as the device path (nlk_solver.cu pressure_solve_projected).
+static int pressure_projected(Ref& R, double* rhs, double tol, double* x) {
+  const size_t N = R.N2; const int mx = R.pr_proj;
+  if (mx <= 0) return uzawa_gmres(R, rhs, tol, x);
+  const int m = (int)R.projX.size();
+  vec xbar(N, 0.0), w(N), wk[3]; for (int c = 0; c < R.d; ++c) wk[c].resize(R.N1);
+  for (int i = 0; i < m; ++i) { const double al = dot(R.projX[i].data(), rhs, N); const double* X = R.projX[i].data(); const double* EX = R.projEX[i].data();
+#pragma omp parallel for schedule(static)
+    for (size_t t = 0; t < N; ++t) { xbar[t] += al * X[t]; rhs[t] -= al * EX[t]; } }
+  int it = uzawa_gmres(R, rhs, tol, x);
+  if (m == mx) {
+    for (size_t t = 0; t < N; ++t) x[t] += xbar[t];
+    apply_E(R, x, w.data(), wk);
+    const double nr = 1.0 / std::sqrt(dot(x, w.data(), N));
+    R.projX.assign(1, vec(x, x + N)); R.projEX.assign(1, w);
+    for (size_t t = 0; t < N; ++t) { R.projX[0][t] *= nr; R.projEX[0][t] *= nr; }
+    return it;
+  }
+  apply_E(R, x, w.data(), wk);
+  vec dl(x, x + N);
+  for (int i = 0; i < m; ++i) { const double be = dot(R.projX[i].data(), w.data(), N); const double* X = R.projX[i].data(); const double* EX = R.projEX[i].data();
+    for (size_t t = 0; t < N; ++t) { dl[t] -= be * X[t]; w[t] -= be * EX[t]; } }
+  const double nn = dot(dl.data(), w.data(), N);
+  if (nn > 0) { const double nr = 1.0 / std::sqrt(nn); for (size_t t = 0; t < N; ++t) { dl[t] *= nr; w[t] *= nr; } R.projX.push_back(dl); R.projEX.push_back(w); }
+  if (m > 0) for (size_t t = 0; t < N; ++t) x[t] += xbar[t];
+  return it;
+}
+
 static void bdf_coeffs(int nbd, double* bd) { bd[0] = bd[1] = bd[2] = bd[3] = 0; if (nbd == 1) { bd[0] = 1; bd[1] = 1; } else if (nbd == 2) { bd[0] = 1.5; bd[1] = 2; bd[2] = -0.5; } else { bd[0] = 11.0 / 6.0; bd[1] = 3; bd[2] = -1.5; bd[3] = 1.0 / 3.0; } }
 static void ab_coeffs(int nab, int nbd, double* ab) {      // Nek setabbd with constant dt
   ab[0] = 1; ab[1] = ab[2] = 0;
@@ -499,7 +529,7 @@ static void advance(Ref& R, int istep) {
   vec rhs(N2), xs(N2);
   { const double* u3[3] = {R.vp[0].data(), R.vp[1].data(), R.vp[2].data()}; opdiv(R, u3, rhs.data(), -1.0); }
   ortho(R, rhs.data());
-  uzawa_gmres(R, rhs.data(), R.ptol, xs.data());
+  pressure_projected(R, rhs.data(), R.ptol, xs.data());
   if (!(R.variant & 1)) R.prlag = R.prp;
   if (!(R.variant & 2)) R.prp = pext;
   for (size_t i = 0; i < N2; ++i) R.prp[i] += (bd[0] / dt) * xs[i];
@@ -572,6 +602,7 @@ void nekref_set_params(void* h, double visc, double rho, int torder, double vtol
   Ref* R = (Ref*)h; R->visc = visc; R->rho = rho; R->torder = torder; R->vtol = vtol; R->ptol = ptol; R->ifheat = ifheat; R->cond = cond; R->rhocp = rhocp; R->ttol = ttol;
   for (int c = 0; c < 3; ++c) R->buoy[c] = buoy[c]; R->fw = fw; R->cg_maxit = cg_maxit; R->gm_maxit = gm_maxit; R->lgmres = lgmres; R->variant = variant;
 }
+void nekref_set_proj(void* h, int pr_proj) { ((Ref*)h)->pr_proj = pr_proj; }
 void nekref_set_mode(void* h, double dt, int adjoint, int nonlinear) { Ref* R = (Ref*)h; R->dt = dt; R->adjoint = adjoint; R->nonlinear = nonlinear; }
 void nekref_set_base(void* h, const double* ux, const double* uy, const double* uz, const double* T) {
   Ref* R = (Ref*)h; const double* u[3] = {ux, uy, uz};
@@ -597,6 +628,7 @@ void nekref_reset_history(void* h) {
   for (int c = 0; c < 3; ++c) { std::fill(R->exx1[c].begin(), R->exx1[c].end(), 0.0); std::fill(R->exx2[c].begin(), R->exx2[c].end(), 0.0); for (int l = 0; l < 2; ++l) std::fill(R->vlag[l][c].begin(), R->vlag[l][c].end(), 0.0); }
   std::fill(R->prlag.begin(), R->prlag.end(), 0.0); for (int l = 0; l < 2; ++l) std::fill(R->tlag[l].begin(), R->tlag[l].end(), 0.0);
   std::fill(R->vg1.begin(), R->vg1.end(), 0.0); std::fill(R->vg2.begin(), R->vg2.end(), 0.0);
+  R->projX.clear(); R->projEX.clear();
 }
 void nekref_advance(void* h, int istep) { advance(*(Ref*)h, istep); }
 void nekref_counters(void* h, int64_t* cg, int64_t* gm) { Ref* R = (Ref*)h; *cg = R->cg_iters; *gm = R->gm_iters; }

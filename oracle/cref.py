@@ -161,9 +161,10 @@ class CRef:
 class CPertStepper:
     """Same interface as oracle.stepper.PertStepper; the state lives in the C++ context."""
 
-    def __init__(self, mesh: SEMesh, prm: StepParams, precond=None, variant=0):
+    def __init__(self, mesh: SEMesh, prm: StepParams, precond=None, variant=0, pr_proj=0):
         self.mesh, self.prm, self.d = mesh, prm, mesh.ndim
         self.ref = CRef(mesh, prm, precond)
+        lib().nekref_set_proj(self.ref.h, C.c_int(pr_proj))
         if variant:
             self.ref.set_params(prm, variant)
         self.adjoint = False; self.nonlinear = False

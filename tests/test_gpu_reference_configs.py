@@ -5,7 +5,7 @@ the C++/OpenMP oracle (oracle/cpp/nekref.cpp; itself checked against the numpy o
     the reference-produced base flow as a fixed point of the nonlinear flow map (KAT-7 on the GPU path);
   * Rayleigh-Benard (examples/rayBen/baseflow fixtures): exptA_temp_linop matvec AND rmatvec;
   * backward-facing step (examples/back_fstep/transient_growth): 60 time steps direct and adjoint (bdf2, filter, SYM);
-  * the synthetic 3-D extruded cylinder of bench.py (lx1 = 8, lxd = 12, two periodic z-layers, 3 992 elements): the stepper
+  * the synthetic 3-D extruded cylinder of bench.py (lx1 = 8, lxd = 12; a 864-element window, three periodic z-layers): the stepper
     itself, not only its kernels, against the oracle.
 Inner tolerances are tightened on both sides (setup_nek takes vtol/ptol: src/neklab_nek_setup.f90:74-75) as SURVEY.md §7
 prescribes for 1e-10 parity of iterative solvers."""
