@@ -187,8 +187,15 @@ int nlk_nonlinear_map(nlk_ctx* c, double tau, double cfl_limit, const nlk_vec* i
  * (src/systems/neklab_systems.f90:229-335; tol_mode 1 / 2).  X is updated in place; rnorm_hist gets niter+1 values. */
 int nlk_newton_fixed_point(nlk_ctx* c, double tau, nlk_vec* X, double tol, int32_t tol_mode, int32_t maxiter, int32_t gmres_kdim,
                            double* rnorm_hist, int32_t* niter, int32_t* info);
-/* neklab_forcing registry (src/neklab_nek_forcing.f90:57-114): constant body force added to the perturbation rhs */
-int nlk_ctx_set_forcing(nlk_ctx* c, const double* fx, const double* fy, const double* fz);
+/* neklab forcing registry (src/neklab_nek_forcing.f90): module arrays neklab_ffx/y/z(lv, lpert+1) added to the body force
+ * inside `userf` through `neklab_forcing(ffx,ffy,ffz,ix,iy,iz,ieg,ipert)` (:96-114).  ipert = 0 is the slot of the nonlinear
+ * solver, ipert = 1 the slot of the perturbation (lpert = 1); any other value is an error (the reference calls nek_end, :44-47).
+ * Host arrays [nel][lx1^ndim]; NULL components are treated as zero (set) or skipped (get). */
+int nlk_set_neklab_forcing(nlk_ctx* c, const double* fx, const double* fy, const double* fz, int32_t ipert);   /* :57-76  */
+int nlk_get_neklab_forcing(nlk_ctx* c, double* fx, double* fy, double* fz, int32_t ipert);                     /* :36-55  */
+int nlk_zero_neklab_forcing(nlk_ctx* c);                                                                       /* :25-34  */
+int nlk_zero_neklab_forcing_ipert(nlk_ctx* c, int32_t ipert);                                                  /* :78-94  */
+int nlk_ctx_set_forcing(nlk_ctx* c, const double* fx, const double* fy, const double* fz);                     /* = set_neklab_forcing(..., ipert = 1) */
 
 /* ------------------------------------------------------------------ analysis entry points (device-resident bases)
  * src/neklab_analysis.f90:38-105 (eigs), :107-156 (svds), :158-212 (newton/gmres). */

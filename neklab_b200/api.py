@@ -56,7 +56,7 @@ nlk_mesh_field nlk_mesh_neighbor nlk_mesh_basis nlk_dense_eig nlk_params_default
 nlk_ctx_set_dt nlk_comm_unique_id nlk_ctx_comm_init nlk_ctx_sync nlk_ctx_stream nlk_vec_create nlk_vec_destroy nlk_vec_copy nlk_vec_zero
 nlk_vec_rand nlk_vec_scal nlk_vec_axpby nlk_vec_dot nlk_vec_norm nlk_vec_size nlk_vec_save_rst nlk_vec_get_rst nlk_vec_nrst
 nlk_vec_clear_rst nlk_vec_upload nlk_vec_download nlk_zvec_scal nlk_zvec_axpby nlk_zvec_dot nlk_basis_innerprod nlk_basis_axpy nlk_basis_dgs nlk_exptA_create
-nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_exptA_time_steps nlk_exptA_set_baseflow nlk_nonlinear_map nlk_newton_fixed_point nlk_ctx_set_forcing nlk_nek2vec nlk_vec2nek
+nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_exptA_time_steps nlk_exptA_set_baseflow nlk_nonlinear_map nlk_newton_fixed_point nlk_ctx_set_forcing nlk_set_neklab_forcing nlk_get_neklab_forcing nlk_zero_neklab_forcing nlk_zero_neklab_forcing_ipert nlk_nek2vec nlk_vec2nek
 nlk_eigs nlk_svds nlk_gmres nlk_test_axhelm nlk_test_dssum nlk_test_opdiv nlk_test_opgradt nlk_test_cdabdtp nlk_test_convect
 nlk_test_convect_adj nlk_test_helmholtz nlk_test_pressure nlk_test_precond nlk_test_cfl nlk_bench_kernel""".split()
 
@@ -291,9 +291,17 @@ class Context:
     def vec2nek(self, vec):
         _chk(lib().nlk_vec2nek(self.h, vec.h))
 
-    def set_forcing(self, f):
+    def set_forcing(self, f, ipert=1):
+        """`set_neklab_forcing(fx, fy, fz, ipert)` (src/neklab_nek_forcing.f90:57-76)."""
         f = [_f64(x) for x in f]
-        _chk(lib().nlk_ctx_set_forcing(self.h, _p(f[0]), _p(f[1]), _p(f[2]) if len(f) > 2 else None))
+        _chk(lib().nlk_set_neklab_forcing(self.h, _p(f[0]), _p(f[1]), _p(f[2]) if len(f) > 2 else None, C.c_int32(ipert)))
+
+    def get_forcing(self, ipert=1):
+        f = [np.zeros(self.mesh.shape1) for _ in range(self.mesh.ndim)]
+        _chk(lib().nlk_get_neklab_forcing(self.h, _p(f[0]), _p(f[1]), _p(f[2]) if len(f) > 2 else None, C.c_int32(ipert))); return f
+
+    def zero_forcing(self, ipert=None):
+        _chk(lib().nlk_zero_neklab_forcing(self.h) if ipert is None else lib().nlk_zero_neklab_forcing_ipert(self.h, C.c_int32(ipert)))
 
     def close(self):
         if self.h:
@@ -452,6 +460,51 @@ class exptA_linop:
             pass
 
 
+# ---- mesh-1 <-> mesh-2 pressure maps and field-file I/O (Nek `mappr` / `load_fld` / `outpost`; src/neklab_utils.f90:305-361)
+def _tensor(M, a, ndim):
+    a = np.einsum("pi,ezyi->ezyp", M, a)
+    a = np.einsum("qj,ezjx->ezqx", M, a)
+    return np.einsum("rk,ekyx->eryx", M, a) if ndim == 3 else a
+
+
+def map12(mesh: Mesh, p1):
+    """mesh 1 (GLL) -> mesh 2 (GL): evaluate the fld pressure at the Gauss points (exact inverse of `map21` for fld pressures)."""
+    n = mesh.lx1
+    return _tensor(mesh.basis("I12").reshape(n - 2, n), _f64(p1), mesh.ndim)
+
+
+def map21(mesh: Mesh, p2):
+    """mesh 2 (GL) -> mesh 1 (GLL): what Nek's `outpost` (prepost.f `mappr`) writes into the P block of a field file."""
+    from .boxmesh import lagrange_interp
+    return _tensor(lagrange_interp(mesh.basis("z1"), mesh.basis("z2")), _f64(p2), mesh.ndim)
+
+
+def load_fld(ctx: Context, path) -> nek_dvector:
+    """`call load_fld(file)` + `nek2vec(bf, vx, vy, vz, pr, t)` (examples/cylinder/stability/direct/1cyl.usr:15-16): read a Nek field
+    file (elements in global-id order), map the pressure onto mesh 2 and upload everything into a device-resident `nek_dvector`."""
+    from .formats import read_fld
+    f = read_fld(path); m = ctx.mesh
+    if f.vel is None or f.vel.shape[0] != m.nel or f.nx != m.lx1:
+        raise NlkError(f"{path}: field file does not match the mesh ({f.nel} elements, nx = {f.nx})")
+    v = ctx.vec()
+    v.upload([f.vel[:, c] for c in range(m.ndim)], map12(m, f.pr) if f.pr is not None else None, f.temp)
+    return v
+
+
+def outpost_dnek(vec: nek_dvector, prefix: str, case: str, index: int = 1, outdir: str = ".", time: float = 0.0, istep: int = 0, wdsize: int = 8):
+    """`outpost_dnek(vec, prefix)` (src/neklab_utils.f90:305-312 -> Nek `outpost`): writes `<prefix><case>0.f%05d` with the X, U, P
+    (mesh 1) and T blocks, readable by Nek's `load_fld`, VisIt/ParaView and the reference's python tools.  Returns the path."""
+    from .formats import write_fld
+    if len(prefix) != 3:
+        raise NlkError("outpost prefix must have 3 characters (Nek convention: 'dir', 'adj', 'BF_', 'nwt', ...)")
+    m = vec.ctx.mesh
+    v, pr, th = vec.download()
+    path = os.path.join(outdir, "%s%s0.f%05d" % (prefix, case, index))
+    write_fld(path, coords=np.stack(m._x, axis=1), vel=np.stack(v, axis=1), pr=map21(m, pr),
+              temp=th if vec.ctx.params.ifheat else None, time=time, istep=istep, wdsize=wdsize)
+    return path
+
+
 def nonlinear_map(ctx: Context, tau, vec_in: nek_dvector, cfl_limit=0.4) -> nek_dvector:
     """`nek_system%response` (src/systems/fixed_point.f90:4-40): F_tau(X) - X."""
     out = nek_dvector(ctx)
@@ -489,7 +542,7 @@ def eigs(A: exptA_linop, nev, kdim, tol=0.0, transpose=False, x0=None, want_vect
     return dict(lam=lr + 1j * li, resid=rs, niter=niter.value, info=info.value, vecs=vecs, history=hist)
 
 
-def linear_stability_analysis_fixed_point(A: exptA_linop, kdim, nev, adjoint=False, outdir=None, tol=0.0, x0=None):
+def linear_stability_analysis_fixed_point(A: exptA_linop, kdim, nev, adjoint=False, outdir=None, tol=0.0, x0=None, case=None):
     """src/neklab_analysis.f90:38-105: eigs, then lambda = log(mu)/tau (:84); writes `eigs_output.txt`
     (6 columns parsed by test/lib/neklabTestCase.py:413-455) and `dir_/adj_eigenspectrum.npy` (n x 3)."""
     lines = []
@@ -497,10 +550,14 @@ def linear_stability_analysis_fixed_point(A: exptA_linop, kdim, nev, adjoint=Fal
     def cb(it, k, lam, res):
         i = int(np.argmax(np.abs(lam)))
         lines.append("%6d %18.10E %18.10E %18.10E %18.10E %s" % (it, lam[i].real, lam[i].imag, abs(lam[i]), res[i], "T" if res[i] < (tol or 3.1622776601683794e-08) else "F"))
-    r = eigs(A, nev, kdim, tol=tol, transpose=adjoint, x0=x0, callback=cb)
+    r = eigs(A, nev, kdim, tol=tol, transpose=adjoint, x0=x0, callback=cb, want_vectors=bool(outdir and case))
     r["eigvals"] = np.log(r["lam"]) / A.tau
     if outdir:
         os.makedirs(outdir, exist_ok=True)
+        if r.get("vecs") and case:                 # outpost_dnek(eigvecs, "dir"|"adj") (src/neklab_analysis.f90:93)
+            for i in range(nev):
+                outpost_dnek(r["vecs"][2 * i], "adj" if adjoint else "dir", case, 2 * i + 1, outdir)
+                outpost_dnek(r["vecs"][2 * i + 1], "adj" if adjoint else "dir", case, 2 * i + 2, outdir)
         with open(os.path.join(outdir, "eigs_output.txt"), "w") as f:
             f.write("  iter            Re                 Im              modulus            residual     conv\n")
             f.write("\n".join(lines) + "\n")

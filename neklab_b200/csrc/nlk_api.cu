@@ -316,16 +316,39 @@ int nlk_ctx_set_dt(nlk_ctx* c, double dt) { if (dt <= 0) { set_error("dt must be
 int nlk_ctx_sync(nlk_ctx* c) { NLK_CUDA(cudaStreamSynchronize(c->st)); NLK_CUDA(cudaGetLastError()); return 0; }
 void* nlk_ctx_stream(nlk_ctx* c) { return (void*)c->st; }
 
-int nlk_ctx_set_forcing(nlk_ctx* c, const double* fx, const double* fy, const double* fz) {
+// neklab forcing registry (src/neklab_nek_forcing.f90): one slot per ipert in 0..lpert (lpert = 1 here)
+static int forcing_slot_ok(int32_t ipert, const char* who) {
+  if (ipert < 0 || ipert > 1) { set_error(std::string(who) + ": invalid value for ipert (0 = nonlinear solver, 1 = perturbation; lpert = 1)"); return 0; }
+  return 1;
+}
+int nlk_set_neklab_forcing(nlk_ctx* c, const double* fx, const double* fy, const double* fz, int32_t ipert) {
+  if (!forcing_slot_ok(ipert, "set_neklab_forcing")) return 1;
   const double* f[3] = {fx, fy, fz};
   for (int k = 0; k < c->dm.ndim; ++k) {
-    if (!c->forcing[k]) { if (dev_alloc(c, &c->forcing[k], c->dm.N1)) return 1; }
-    if (f[k]) NLK_CUDA(cudaMemcpyAsync(c->forcing[k], f[k], c->dm.N1 * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    else NLK_CUDA(cudaMemsetAsync(c->forcing[k], 0, c->dm.N1 * sizeof(double), c->st));
+    if (!c->forcing[ipert][k]) { if (dev_alloc(c, &c->forcing[ipert][k], c->dm.N1)) return 1; }
+    if (f[k]) NLK_CUDA(cudaMemcpyAsync(c->forcing[ipert][k], f[k], c->dm.N1 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    else NLK_CUDA(cudaMemsetAsync(c->forcing[ipert][k], 0, c->dm.N1 * sizeof(double), c->st));
   }
   NLK_CUDA(cudaStreamSynchronize(c->st));
-  c->has_forcing = true; return 0;
+  c->has_forcing[ipert] = true; return 0;
 }
+int nlk_get_neklab_forcing(nlk_ctx* c, double* fx, double* fy, double* fz, int32_t ipert) {
+  if (!forcing_slot_ok(ipert, "get_neklab_forcing")) return 1;
+  double* f[3] = {fx, fy, fz};
+  for (int k = 0; k < c->dm.ndim; ++k) {
+    if (!f[k]) continue;
+    if (c->has_forcing[ipert]) NLK_CUDA(cudaMemcpyAsync(f[k], c->forcing[ipert][k], c->dm.N1 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    else std::memset(f[k], 0, c->dm.N1 * sizeof(double));
+  }
+  NLK_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+int nlk_zero_neklab_forcing_ipert(nlk_ctx* c, int32_t ipert) {
+  if (!forcing_slot_ok(ipert, "zero_neklab_forcing_ipert")) return 1;
+  c->has_forcing[ipert] = false; return 0;            // a zero slot is skipped by the step (same arithmetic as adding zeros)
+}
+int nlk_zero_neklab_forcing(nlk_ctx* c) { c->has_forcing[0] = c->has_forcing[1] = false; return 0; }
+int nlk_ctx_set_forcing(nlk_ctx* c, const double* fx, const double* fy, const double* fz) { return nlk_set_neklab_forcing(c, fx, fy, fz, 1); }
 
 // ============================================================================================== nek_dvector
 int nlk_vec_create(nlk_ctx* c, nlk_vec** out) {

@@ -98,8 +98,8 @@ struct nlk_ctx {
   double* tlag[2] = {nullptr, nullptr};
   double* vgradt1 = nullptr, *vgradt2 = nullptr;
   double* bf[3] = {nullptr}, *bq = nullptr;
-  double* forcing[3] = {nullptr, nullptr, nullptr};
-  bool has_forcing = false;
+  double* forcing[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // neklab_ffx/y/z(lv, lpert+1): slot 0 nonlinear solver, slot 1 perturbation
+  bool has_forcing[2] = {false, false};
   // work
   double* wk[8] = {nullptr};             // N1 each
   double* cg_x = nullptr, *cg_r = nullptr, *cg_p = nullptr, *cg_w = nullptr;

@@ -460,7 +460,8 @@ int step_advance(nlk_ctx* c, int istep) {
   // ---- igeom = 1: makefp = makeufp + advabp(_adjoint) + makextp + makebdfp ; lagfieldp
   for (int k = 0; k < d; ++k) {
     const double* f0 = (P.ifheat && P.buoyancy[k] != 0.0 && !c->adjoint) ? c->tp : nullptr;      // adjoint: the buoyancy coupling moves to the temperature equation
-    const double* f1 = c->has_forcing ? c->forcing[k] : nullptr;
+    const int fslot = c->nonlinear ? 0 : 1;                                 // neklab_forcing(..., ipert = jp): neklab_nek_forcing.f90:96-114
+    const double* f1 = c->has_forcing[fslot] ? c->forcing[fslot][k] : nullptr;
     if (f0 || f1) launch_lin(c->bf[k], dm.N1, P.buoyancy[k], f0, 1.0, f1, 0, nullptr, 0, nullptr, dm.bm1, st);
     else NLK_CUDA(cudaMemsetAsync(c->bf[k], 0, dm.N1 * sizeof(double), st));
   }

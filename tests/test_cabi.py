@@ -146,3 +146,32 @@ def test_no_cpu_fallback(nlk_lib):
     m = nlk_mesh(om)
     with pytest.raises(api.NlkError, match="no usable CUDA device"):
         api.Context(m, api.default_params())
+
+
+def test_fortran_shim_binds_only_exported_symbols(nlk_lib):
+    """fortran/neklab_b200.f90 cannot be compiled here (no Fortran compiler in the image): check mechanically that every
+    bind(C, name=...) it declares is exported by libnlk.so and declared in include/nlk.h, and that the interoperable
+    derived types list the fields of the C structs in order."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "fortran", "neklab_b200.f90")).read()
+    hdr = open(os.path.join(root, "include", "nlk.h")).read()
+    names = sorted(set(re.findall(r'bind\(C,\s*name="(\w+)"\)', src)))
+    assert len(names) >= 50
+    for nm in names:
+        assert hasattr(nlk_lib, nm), nm
+        assert re.search(r"\b%s\s*\(" % nm, hdr), nm
+    # nlk_params field order (Fortran sequence association with the C struct)
+    cblk = hdr[hdr.index("typedef struct {\n  double viscosity"):hdr.index("} nlk_params;")]
+    cblk = re.sub(r"/\*.*?\*/", "", cblk, flags=re.S)
+    c_fields = []
+    for decl in re.findall(r"\b(?:double|int32_t)\s+([^;]+);", cblk):
+        c_fields += [w.strip().split("[")[0] for w in decl.split(",")]
+    fblk = src[src.index("type, bind(C) :: nlk_params"):]
+    fblk = fblk[:fblk.index("end type")]
+    f_fields = []
+    for line in fblk.splitlines()[1:]:
+        if "::" in line:
+            f_fields += [w.strip().split("(")[0] for w in line.split("::")[1].split(",")]
+    assert f_fields == c_fields, (f_fields, c_fields)

@@ -83,3 +83,67 @@ def test_reference_step_and_convection_cell_files():
     assert (f.nx, f.nel, f.rdcode) == (10, 40, "XUPT") and f.temp is not None
     assert np.abs(f.temp - 2.0 * (1.0 - f.coords[:, 1])).max() < 1e-5                        # shipped state: linear conduction profile, T = 2 (1 - y)
     assert rb.cbc.shape[0] == 2 and set(np.unique(rb.cbc[1]).tolist()) == {"E  ", "P  ", "t  "}
+
+
+def test_pressure_maps_between_mesh1_and_mesh2(nlk_lib):
+    """`map12` / `map21` of the PRODUCT (neklab_b200.api; Nek `mappr`): mesh-2 -> mesh-1 -> mesh-2 is the identity (KAT-2: the fld
+    pressure is exactly of degree lx2-1) and both agree with the oracle's maps."""
+    from neklab_b200 import api
+    from oracle import ops
+    from tests.util import box_case, nlk_mesh
+    for ndim, nel in ((2, (3, 2)), (3, (2, 2, 2))):
+        om, _, _ = box_case(ndim=ndim, nel=nel, n=6, lxd=9)
+        m = nlk_mesh(om)
+        p2 = np.random.default_rng(ndim).standard_normal(om.bm2.shape)
+        assert np.abs(api.map12(m, api.map21(m, p2)) - p2).max() < 1e-13
+        assert np.abs(api.map21(m, p2) - ops.map21(om, p2)).max() < 1e-13
+        assert np.abs(api.map12(m, om.bm1) - ops.map12(om, om.bm1)).max() < 1e-13
+
+
+def _parse_like_the_reference(logfile):
+    """Transcription of the parsing RULES of the reference harness (test/lib/neklabTestCase.py:413-455): split on blanks, skip
+    lines with < 6 tokens or non-numeric columns 2-5, keep the lines whose 6th token is 'T', label them lambda_1, lambda_2, ..."""
+    eigs = {}
+    for line in open(logfile):
+        parts = line.split()
+        if len(parts) < 6:
+            continue
+        try:
+            re_, im_, mod, res = (float(parts[i]) for i in (1, 2, 3, 4))
+        except ValueError:
+            continue
+        if parts[5] == "T":
+            eigs["lambda_%d" % (len(eigs) + 1)] = dict(Re=re_, Im=im_, modulus=mod, residual=res)
+    return eigs
+
+
+@pytest.mark.gpu
+def test_outpost_load_round_trip_and_eigs_output_format(nlk_lib, tmp_path):
+    """(f)2: `outpost_dnek` writes a field file `load_fld` (ours and Nek's layout) reads back bit-exactly, pressure mapped mesh 2 ->
+    mesh 1 -> mesh 2; `linear_stability_analysis_fixed_point` writes `eigs_output.txt` / `dir_eigenspectrum.npy` that the reference's
+    own parser rules accept (test/lib/neklabTestCase.py:413-455; poiseuille.usr:30-36 for the npy layout)."""
+    from neklab_b200 import api
+    from oracle.stepper import seeded_field
+    from tests.util import box_case, nlk_mesh
+    om, _, _ = box_case(ndim=2, nel=(4, 3), n=6, lxd=9, bc={"xlo": "v  ", "xhi": "O  "})
+    ctx = api.Context(nlk_mesh(om), api.default_params(viscosity=0.05, torder=3, vtol=1e-11, ptol=1e-10, gmres_maxit=500))
+    x0 = seeded_field(om, 3); x0.pr = np.random.default_rng(1).standard_normal(om.bm2.shape)
+    v = ctx.vec(); v.upload(x0.v, x0.pr)
+    path = api.outpost_dnek(v, "BF_", "box", 1, str(tmp_path), time=1.0, istep=101)
+    assert os.path.basename(path) == "BF_box0.f00001"
+    f = read_fld(path)
+    assert f.rdcode == "XUP" and f.istep == 101 and np.array_equal(f.coords, om.coords) and np.array_equal(f.vel[:, 0], x0.v[0])
+    w = api.load_fld(ctx, path)
+    wv, wp, _ = w.download()
+    assert np.array_equal(wv[1], x0.v[1]) and np.abs(wp - x0.pr).max() < 1e-12
+    # analysis driver output files
+    x = om.coords
+    bf = ctx.vec(); bf.upload([1.0 + 0.3 * np.sin(0.5 * x[:, 1]), 0.2 * np.cos(0.4 * x[:, 0])])
+    A = api.exptA_linop(ctx, 0.1, bf); A.init()
+    r = api.linear_stability_analysis_fixed_point(A, 12, 2, outdir=str(tmp_path), tol=1e-3, case="box")
+    got = _parse_like_the_reference(str(tmp_path / "eigs_output.txt"))
+    assert "lambda_1" in got and abs(got["lambda_1"]["modulus"] - abs(r["lam"][0])) < 1e-9 * abs(r["lam"][0])
+    spec = np.load(str(tmp_path / "dir_eigenspectrum.npy"))
+    assert spec.shape == (2, 3) and np.allclose(spec[:, 0] + 1j * spec[:, 1], np.log(r["lam"]) / 0.1)
+    assert os.path.exists(str(tmp_path / "dirbox0.f00001")) and read_fld(str(tmp_path / "dirbox0.f00001")).rdcode == "XUP"
+    ctx.close()

@@ -141,3 +141,33 @@ def test_svds_vectors_and_zvector(small):
     ref = [(0.3 - 0.7j) * ref2[k] + (1.1 + 0.2j) * ref1[k] for k in range(2)]
     vr, _, _ = z1.re.download(); vi, _, _ = z1.im.download()
     assert rel(vr[0], ref[0].real) < 1e-13 and rel(vi[1], ref[1].imag) < 1e-13
+
+
+def test_eigs_with_forced_krylov_schur_restarts(nlk_lib):
+    """LightKrylov `eigs` restarts (krylov_schur): kdim = 10 forces several restarts before nev = 2 Ritz pairs
+    converge.  The oracle reorders the real Schur form of H (LightKrylov's construction); the device path keeps an orthonormal
+    basis of the SAME invariant subspace (selected Ritz values: |lambda| above the median, conjugate pairs together) -- an
+    orthogonal change of basis of the Krylov-Schur decomposition, so the Ritz values must agree.  Run with the consistent
+    restart-field arithmetic (rst_mode 1) on both sides so that the operator is one fixed linear map."""
+    from neklab_b200 import api
+    from oracle.cref import CPertStepper
+    om, _, _ = box_case(ndim=2, nel=(4, 3), n=6, lxd=9, bc={"xlo": "v  ", "xhi": "O  "})
+    x = om.coords
+    bf = NekVec(om, 3); bf.v = [1.0 + 0.3 * np.sin(0.5 * x[:, 1]), 0.2 * np.cos(0.4 * x[:, 0])]
+    kw = dict(viscosity=0.05, torder=3, vtol=1e-13, ptol=1e-13, gmres_maxit=2000, cg_maxit=2000)
+    A_or = ExptA(CPertStepper(om, StepParams(**kw), precond=SchwarzCoarse(om)), 0.2, bf)
+    x0 = seeded_field(om, 7)
+    niter_or = []
+    NekVec.RST_MODE = 1
+    try:
+        lam_or, res_or, *_ = eigs_or(A_or.matvec, x0, nev=2, kdim=10, tol=1e-8, maxiter=25, log=lambda it, k, lam, res: niter_or.append(it))
+    finally:
+        NekVec.RST_MODE = 0
+    assert niter_or[-1] > 10                                   # at least one restart happened
+    ctx = api.Context(nlk_mesh(om), api.default_params(rst_mode=1, **kw))
+    A = api.exptA_linop(ctx, 0.2, _dev(ctx, bf))
+    r = api.eigs(A, nev=2, kdim=10, tol=1e-8, x0=_dev(ctx, x0))
+    assert r["info"] == 0 and r["niter"] > 10
+    assert abs(abs(r["lam"][0]) - abs(lam_or[0])) < 1e-8 * abs(lam_or[0])
+    assert abs(r["lam"][0].real - lam_or[0].real) < 1e-8 and abs(abs(r["lam"][0].imag) - abs(lam_or[0].imag)) < 1e-8
+    ctx.close()

@@ -129,34 +129,10 @@ def orr_sommerfeld_leading(R, N=120):
 
 def synth3d_window(half_width=3.0, layers=3, n=8, lxd=12):
     """A window of bench.py's synthetic 3-D config (the Re=50 cylinder mesh extruded periodically in z, lx1 = 8, lxd = 12):
-    the 2-D elements whose centroid lies within `half_width` of the cylinder, `layers` periodic z-layers.  Cut faces become
-    'v  ' (inflow side and lateral) or 'O  ' (downstream side), so the curved near-cylinder elements, the periodic direction
-    and an outflow boundary are all present.  Returns (SEMesh, U list) for the oracle; `nlk_mesh(om)` gives the device mesh."""
+    the 2-D elements whose centroid lies within `half_width` of the cylinder (`bench.window_case`: cut faces become 'v  ' or,
+    downstream, 'O  '), `layers` periodic z-layers -- curved near-cylinder elements, the periodic direction and an outflow
+    boundary are all present.  Returns (SEMesh, U list) for the oracle; `nlk_mesh(om)` gives the device mesh."""
     import bench
-    case = bench.cylinder_inputs()
-    c = case["coords"]; E = c.shape[0]
-    cen = c[:, :, 0].reshape(E, 2, -1).mean(axis=2)
-    sel = np.where((np.abs(cen[:, 0] - 0.5) < half_width) & (np.abs(cen[:, 1]) < half_width))[0]
-    vert = case["vertex"][sel]
-    uniq, inv = np.unique(vert, return_inverse=True)
-    vert = (inv.reshape(vert.shape) + 1).astype(np.int64)
-    cbc = case["cbc"][sel].copy()
-    # faces (preprocessor order) -> lexicographic corner pairs
-    fc = {0: (0, 1), 1: (1, 3), 2: (2, 3), 3: (0, 2)}
-    keys = {}
-    for e in range(len(sel)):
-        for f, (a, b) in fc.items():
-            keys.setdefault(tuple(sorted((vert[e, a], vert[e, b]))), []).append((e, f))
-    xs = c[sel][:, 0, 0]
-    fidx = {0: (0, slice(None)), 1: (slice(None), -1), 2: (-1, slice(None)), 3: (slice(None), 0)}
-    xcut = max(xs[e][fidx[f]].mean() for lst in keys.values() if len(lst) == 1 for e, f in lst)
-    for lst in keys.values():
-        if len(lst) == 1:
-            e, f = lst[0]
-            if cbc[e, f] != "E  ":
-                continue
-            cbc[e, f] = "O  " if xs[e][fidx[f]].mean() > xcut - 1e-6 else "v  "
-    sub = dict(coords=c[sel], vel=case["vel"][sel], vertex=vert, cbc=cbc)
-    coords, U, vertex, cbc3 = bench.extrude(sub, n, layers)
+    coords, U, vertex, cbc3 = bench.extrude(bench.window_case(bench.cylinder_inputs(), half_width), n, layers)
     om = SEMesh(coords, vertex, cbc3, lxd)
     return om, [U[:, k].copy() for k in range(3)]
