@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnlk.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["nlk_basis.cpp", "nlk_mesh.cpp", "nlk_dense.cpp", "nlk_kernels.cu", "nlk_kernels_tp.cu", "nlk_solver.cu", "nlk_api.cu", "nlk_krylov.cu", "nlk_coarse.cu", "nlk_cgp.cu", "nlk_cg3.cu"]
+SOURCES = ["nlk_basis.cpp", "nlk_mesh.cpp", "nlk_dense.cpp", "nlk_kernels.cu", "nlk_kernels_tp.cu", "nlk_solver.cu", "nlk_api.cu", "nlk_krylov.cu", "nlk_coarse.cu", "nlk_cgp.cu", "nlk_schwarz.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fopenmp,-O3", "-Xcudafe", "--diag_suppress=177"]
 

@@ -201,6 +201,7 @@ static int ctx_setup(nlk_ctx* c) {
     launch_schwarz_gather_nowt(dm, c->sw_z, c->sw_t, dm.swt, c->st);
     launch_recip(dm.swt, dm.swt, N2, c->st);
     c->have_schwarz = true;
+    if (swf_setup(c)) return 1;
     // coarse operator A0 = R0 E R0^T, column by column on the device; dense inverse on the host
     const int64_t nvt = hm.nvert;
     if (nvt <= 5000 && c->prm.precond != 2 && c->prm.precond != 4) {
@@ -302,7 +303,7 @@ int nlk_ctx_destroy(nlk_ctx* c) {
     for (cudaEvent_t e : c->ph.pool) cudaEventDestroy(e);
   }
   if (c->crs_graph) cudaGraphExecDestroy(c->crs_graph);
-  cg3_release(c);
+  swf_release(c);
   for (void* p : c->allocs) cudaFree(p);
   if (c->h_sc) cudaFreeHost(c->h_sc);
   if (c->h_red) cudaFreeHost(c->h_red);
@@ -782,6 +783,7 @@ int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_lau
       case 5: { CPtr4 A{{c->wk[0], c->wk[1], c->wk[2], nullptr}}; launch_dot(dm.N1, A, A, d, dm.bm1, c->d_red, c->red, c->st); break; }
       case 6: if (!c->coarse_sparse) { set_error("bench 6: the context has no sparse coarse level"); return 1; } return coarse_solve_sparse(c, c->crs_r, c->crs_y);
       case 7: if (!c->have_schwarz) { set_error("bench 7: no Schwarz level"); return 1; }      // Schwarz branch alone
+              if (c->swf) return swf_apply(c, c->pw[3], nullptr, nullptr, c->pw[4]);
               launch_schwarz_embed(dm, c->pw[3], nullptr, c->sw_w, c->st); if (ctx_gs(c, Ptr3{{c->sw_w, nullptr, nullptr}}, 1)) return 1;
               launch_schwarz_fdm(dm, c->sw_w, c->sw_z, c->sw_t, c->st); if (ctx_gs(c, Ptr3{{c->sw_t, nullptr, nullptr}}, 1)) return 1;
               launch_schwarz_gather(dm, c->sw_z, c->sw_t, c->pw[4], c->st); break;
@@ -818,7 +820,7 @@ int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_lau
     case 4: bytes = 2 * 8.0 * N2 + 6 * 8.0 * N1; break;
     case 5: bytes = (d + 1) * 8.0 * N1; break;
     case 6: bytes = (double)c->crs_iters * (12.0 * (double)c->crs_nnz + 9 * 8.0 * (double)dm.nvert); break;   // CSR values + indices per SpMV, vectors
-    case 7: bytes = 2 * 8.0 * N2 + 6 * 8.0 * N1; break;
+    case 7: bytes = 2 * 8.0 * N2 + 6 * 8.0 * N1; break;                       // (same figure for the chain and the fused path: the chain's work arrays)
     case 8: bytes = (5 + dm.ng + 1) * 8.0 * N1; break;                       // r, hd, p in; p, w out; g-factors; bm1
     case 9: bytes = 8 * 8.0 * N1; break;                                     // x, r, p, w, wa, wb in; x, r out
     case 10: bytes = d * 8.0 * N1 + (1 + d * d) * 8.0 * N2; break;

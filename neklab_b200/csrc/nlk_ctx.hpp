@@ -116,7 +116,7 @@ struct nlk_ctx {
   double* crs_p = nullptr, *crs_q = nullptr, *crs_z = nullptr, *crs_rr = nullptr;
   double* cg_hd[4] = {nullptr, nullptr, nullptr, nullptr}, *cg_wa[4] = {nullptr, nullptr, nullptr, nullptr}, *cg_wb[4] = {nullptr, nullptr, nullptr, nullptr};
   double cg_key_h1[4] = {0, 0, 0, 0}, cg_key_h2[4] = {0, 0, 0, 0};           // (h1, h2) the weights of mask slot k were built for (lazily allocated)
-  void* cg3 = nullptr;                      // state of the opt-in three-field PCG (nlk_cg3.cu), released by cg3_release
+  void* swf = nullptr;                      // fused Schwarz branch: pull tables + compact face buffers (nlk_schwarz.cu), released by swf_release
   double* cg_pap_partial = nullptr; unsigned int* cg_pap_counter = nullptr;   // block partials of p.Ap reduced inside the Helmholtz kernel
   double* crs_partial = nullptr;         // per-block partial sums of the coarse PCG (own scratch: the solve runs on the side stream)
   cudaGraphExec_t crs_graph = nullptr; const double* crs_graph_in = nullptr; double* crs_graph_out = nullptr;   // the fixed-count PCG as one graph launch
@@ -158,10 +158,10 @@ int step_setup_cfl(nlk_ctx* c, double tau, double cfl_limit, CPtr3 u);
 int step_advance(nlk_ctx* c, int istep);
 int helmholtz_solve(nlk_ctx* c, double* rhs_local, double h1, double h2, const double* mask, double tol, double* x, int* iters);
 int cg_weights(nlk_ctx* c, const double* mask, double h1, double h2, int* slot_out);
-// opt-in three-field lockstep PCG (nlk_cg3.cu; NLK_CG3=1)
-bool cg3_enabled();
-void cg3_release(nlk_ctx* c);
-int helmholtz_solve3(nlk_ctx* c, int nf, double* const* rhs, double h1, double h2, const double* const* masks, double tol, double* const* sol);
+// fused Schwarz branch of the pressure preconditioner (nlk_schwarz.cu)
+int swf_setup(nlk_ctx* c);
+void swf_release(nlk_ctx* c);
+int swf_apply(nlk_ctx* c, const double* r, const double* in_mul, const double* yc, double* z, cudaEvent_t wait_before_b = nullptr);
 int helmholtz_solve_multi(nlk_ctx* c, int nf, double* const* rhs_local, double h1, double h2, const double* const* masks, double tol, double* const* sol);
 int sync_cg_counter(nlk_ctx* c);
 int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* iters);

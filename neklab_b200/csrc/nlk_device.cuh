@@ -157,6 +157,12 @@ void launch_cg_finalize(SolverScal* sc, int which, double vol, cudaStream_t st);
 bool tp_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, const double* in_mul, const double* out_mul, cudaStream_t st);
 bool tp_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st);
 bool tp_schwarz_fdm(const DevMesh& dm, const double* w, double* z, double* t, cudaStream_t st);
+// fused Schwarz with pull tables (nlk_kernels_tp.cu; orchestration in nlk_schwarz.cu)
+bool tp_swf_a(const DevMesh& dm, const double* r, const double* mul, const int32_t* t1, const double* ghost, double* zint, double* ZF, cudaStream_t st);
+bool tp_swf_b(const DevMesh& dm, const double* zint, const double* ZF, const int32_t* t2, const double* ghost, const double* yc, double* out, cudaStream_t st);
+void launch_coarse_part_w(const DevMesh& dm, const double* r, const double* mul, double* part, cudaStream_t st);
+void launch_swf_pack(const double* src, const double* mul, const int32_t* idx, int n, double* out, cudaStream_t st);
+void launch_vert_gather(const DevMesh& dm, const double* part, double* rc, cudaStream_t st);
 bool tp_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double alpha, int accumulate, cudaStream_t st);
 bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st, int nj);
 extern thread_local long g_launches;   // counts kernel launches issued through these wrappers

@@ -914,6 +914,9 @@ __global__ void k_vert_gather(const double* __restrict__ part, const int32_t* __
   for (int t = off[v]; t < off[v + 1]; ++t) s += part[ec[t]];
   rc[v] = s;
 }
+void launch_vert_gather(const DevMesh& dm, const double* part, double* rc, cudaStream_t st) {
+  k_vert_gather<<<cdiv(dm.nvert, 128), 128, 0, st>>>(part, dm.vert_off, dm.vert_ec, rc, dm.nvert); LAUNCH_COUNT();
+}
 void launch_coarse_restrict(const DevMesh& dm, const double* r, const double* mul, double* part, double* rc, cudaStream_t st) {
   size_t nec = (size_t)dm.E << dm.ndim;
   k_coarse_part<<<cdiv(nec, 128), 128, 0, st>>>(r, mul, part, dm.w2 + dm.q, dm.q, dm.ndim, nec); LAUNCH_COUNT();

@@ -604,6 +604,129 @@ __global__ void k_schwarz_fdm_t(const double* __restrict__ w, double* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K10 fused Schwarz (pull tables)
+// The overlap exchange of the additive Schwarz smoother only ever moves FACE-INTERIOR values between the two elements that
+// share a face (multiplicity 2), so "dssum, then subtract the own copy" is a pairwise fetch.  With two precomputed index
+// tables per (element, face, slot) -- t1: where the neighbour's first interior pressure layer lives in the residual array,
+// t2: where the neighbour's extended-layer FDM value lives in the compact face array ZF (negative = ghost slot of another
+// rank, -1 = no neighbour) -- the five-kernel chain embed -> dssum -> fdm -> dssum -> gather over three velocity-sized
+// work arrays becomes two kernels over pressure-sized ones:
+//   A: z = (S (x) S (x) S) dinv (S^T (x) S^T (x) S^T) [r_e extended by the neighbours' layers]  -> zint (q^d), ZF (2d x q^(d-1))
+//   B: out = wt * (zint + neighbours' ZF on the first interior layer) [+ coarse prolongation]
+template <int N, int DIM>
+__device__ __forceinline__ void swf_face_of(int i, int j, int k, int& f, int& s, int& nb) {
+  constexpr int q = N - 2;
+  const bool bi = (i == 0 || i == N - 1), bj = (j == 0 || j == N - 1), bk = DIM == 3 && (k == 0 || k == N - 1);
+  nb = (int)bi + (int)bj + (int)bk;
+  if (bi) { f = (i == 0 ? 0 : 1); s = (j - 1) + q * (k - (DIM == 3 ? 1 : 0)); }
+  else if (bj) { f = 2 + (j == 0 ? 0 : 1); s = (i - 1) + q * (k - (DIM == 3 ? 1 : 0)); }
+  else { f = 4 + (k == 0 ? 0 : 1); s = (i - 1) + q * (j - 1); }
+}
+template <int N, int DIM>
+__global__ void k_swf_a(const double* __restrict__ r, const double* __restrict__ mul, const int32_t* __restrict__ t1, const double* __restrict__ ghost,
+                        const double* __restrict__ S, const double* __restrict__ St, const double* __restrict__ dinv,
+                        double* __restrict__ zint, double* __restrict__ ZF) {
+  constexpr int n = N, q = N - 2, d = DIM, nz = DIM == 3 ? N : 1, np1 = n * n * nz, nn = n * n, qz = DIM == 3 ? q : 1, np2 = q * q * qz;
+  constexpr int NF = 2 * DIM, FS = DIM == 3 ? q * q : q;
+  constexpr int PN = DIM == 3 ? (n | 1) : n, npP = PN * n * nz;
+  extern __shared__ double sm[];
+  double* sS = sm; double* sSt = sS + d * nn; double* A = sSt + d * nn; double* B = A + npP;
+  const size_t e = blockIdx.x;
+  load_mat_t(sS, S + e * (size_t)d * nn, d * nn); load_mat_t(sSt, St + e * (size_t)d * nn, d * nn);
+  const int32_t* te = t1 + e * (size_t)(NF * FS);
+  for (int p = threadIdx.x; p < np1; p += blockDim.x) {
+    const int i = p % n, j = (p / n) % n, k = DIM == 3 ? p / nn : 0;
+    int f, s_, nb; swf_face_of<N, DIM>(i, j, k, f, s_, nb);
+    double v = 0.0;
+    if (nb == 0) { const size_t g = e * np2 + (size_t)((DIM == 3 ? (k - 1) * q : 0) + (j - 1)) * q + (i - 1); v = mul ? r[g] * mul[g] : r[g]; }
+    else if (nb == 1) { const int idx = te[f * FS + s_]; if (idx >= 0) v = mul ? r[idx] * mul[idx] : r[idx]; else if (idx <= -2) v = ghost[-2 - idx]; }
+    A[i + PN * (p / n)] = v;
+  }
+  __syncthreads();
+  double* res;
+  contract_t<n, n, 0, false, n, n, nz, MAT_SMEM, PN, PN>(B, A, sSt);
+  contract_t<n, n, 1, false, n, n, nz, MAT_SMEM, PN, PN>(A, B, sSt + nn);
+  if constexpr (DIM == 3) {
+    contract_t<n, n, 2, false, n, n, nz, MAT_SMEM, PN, PN>(B, A, sSt + 2 * nn);
+    for (int p = threadIdx.x; p < np1; p += blockDim.x) B[(p % n) + PN * (p / n)] *= dinv[e * np1 + p];
+    __syncthreads();
+    contract_t<n, n, 0, false, n, n, nz, MAT_SMEM, PN, PN>(A, B, sS);
+    contract_t<n, n, 1, false, n, n, nz, MAT_SMEM, PN, PN>(B, A, sS + nn);
+    contract_t<n, n, 2, false, n, n, nz, MAT_SMEM, PN, PN>(A, B, sS + 2 * nn);
+    res = A;
+  } else {
+    for (int p = threadIdx.x; p < np1; p += blockDim.x) A[p] *= dinv[e * np1 + p];
+    __syncthreads();
+    contract_t<n, n, 0, false, n, n, nz>(B, A, sS);
+    contract_t<n, n, 1, false, n, n, nz>(A, B, sS + nn);
+    res = A;
+  }
+  for (int p = threadIdx.x; p < np1; p += blockDim.x) {
+    const int i = p % n, j = (p / n) % n, k = DIM == 3 ? p / nn : 0;
+    int f, s_, nb; swf_face_of<N, DIM>(i, j, k, f, s_, nb);
+    const double v = res[i + PN * (p / n)];
+    if (nb == 0) zint[e * np2 + (size_t)((DIM == 3 ? (k - 1) * q : 0) + (j - 1)) * q + (i - 1)] = v;
+    else if (nb == 1) ZF[e * (size_t)(NF * FS) + f * FS + s_] = v;
+  }
+}
+template <int N, int DIM>
+__global__ void k_swf_b(const double* __restrict__ zint, const double* __restrict__ ZF, const int32_t* __restrict__ t2, const double* __restrict__ ghost,
+                        const double* __restrict__ wt, const double* __restrict__ yc, const int64_t* __restrict__ vertex,
+                        const double* __restrict__ z2, double* __restrict__ out, size_t N2) {
+  constexpr int q = N - 2, qz = DIM == 3 ? q : 1, np2 = q * q * qz, NF = 2 * DIM, FS = DIM == 3 ? q * q : q, NV = 1 << DIM;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < N2; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = g / np2; const int p = (int)(g - e * np2);
+    const int i = p % q, j = (p / q) % q, k = DIM == 3 ? p / (q * q) : 0;
+    const int32_t* te = t2 + e * (size_t)(NF * FS);
+    double v = zint[g];
+    auto add = [&](int f, int s_) { const int idx = te[f * FS + s_]; if (idx >= 0) v += ZF[idx]; else if (idx <= -2) v += ghost[-2 - idx]; };
+    if (i == 0) add(0, j + q * k);
+    if (i == q - 1) add(1, j + q * k);
+    if (j == 0) add(2, i + q * k);
+    if (j == q - 1) add(3, i + q * k);
+    if (DIM == 3) { if (k == 0) add(4, i + q * j); if (k == q - 1) add(5, i + q * j); }
+    v *= wt[g];
+    if (yc) {
+      const double hx1 = 0.5 * (1 + z2[i]), hy1 = 0.5 * (1 + z2[j]), hz1 = DIM == 3 ? 0.5 * (1 + z2[k]) : 1.0;
+      const int64_t* ve = vertex + e * NV;
+      double s = 0;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        const double h = ((c & 1) ? hx1 : 1 - hx1) * (((c >> 1) & 1) ? hy1 : 1 - hy1) * (DIM == 3 ? (((c >> 2) & 1) ? hz1 : 1 - hz1) : 1.0);
+        s += h * yc[ve[c] - 1];
+      }
+      v += s;
+    }
+    out[g] = v;
+  }
+}
+// coarse restriction, one warp per element: part[e][c] = sum_p shape_c(p) r[e][p] (* mul), coalesced
+template <int DIM>
+__global__ void k_coarse_part_w(const double* __restrict__ r, const double* __restrict__ mul, double* __restrict__ part, const double* __restrict__ z2, int q, int64_t E) {
+  constexpr int NV = 1 << DIM;
+  const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= E) return;
+  const int np2 = DIM == 3 ? q * q * q : q * q;
+  double acc[NV];
+#pragma unroll
+  for (int c = 0; c < NV; ++c) acc[c] = 0.0;
+  for (int p = lane; p < np2; p += 32) {
+    const size_t g = (size_t)e * np2 + p;
+    const double v = mul ? r[g] * mul[g] : r[g];
+    const int i = p % q, j = (p / q) % q, k = DIM == 3 ? p / (q * q) : 0;
+    const double hx1 = 0.5 * (1 + z2[i]), hy1 = 0.5 * (1 + z2[j]), hz1 = DIM == 3 ? 0.5 * (1 + z2[k]) : 1.0;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) acc[c] += v * ((c & 1) ? hx1 : 1 - hx1) * (((c >> 1) & 1) ? hy1 : 1 - hy1) * (DIM == 3 ? (((c >> 2) & 1) ? hz1 : 1 - hz1) : 1.0);
+  }
+#pragma unroll
+  for (int c = 0; c < NV; ++c) { double t = acc[c]; for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o); if (lane == 0) part[e * NV + c] = t; }
+}
+__global__ void k_swf_pack(const double* __restrict__ src, const double* __restrict__ mul, const int32_t* __restrict__ idx, int n, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) { const int g = idx[t]; out[t] = mul ? src[g] * mul[g] : src[g]; }
+}
+
 // ------------------------------------------------------------------------------------------------ dispatch
 #define TP_CASE_N(N_) \
   case N_ * 10 + 2: FN(N_, 2); break; \
@@ -687,6 +810,33 @@ bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha,
   TP_SWITCH_NM((dm.n * 100 + dm.m) * 10 + dm.ndim)
 #undef FN
   ++g_launches; return true;
+}
+
+bool tp_swf_a(const DevMesh& dm, const double* r, const double* mul, const int32_t* t1, const double* ghost, double* zint, double* ZF, cudaStream_t st) {
+  const size_t npP = dm.ndim == 3 ? (size_t)(dm.n | 1) * dm.n * dm.n : (size_t)dm.np1;
+  size_t smem = (size_t)(2 * dm.ndim * dm.n * dm.n + 2 * npP) * sizeof(double);
+  int thr = tp_threads(dm.n, dm.ndim, dm.np1);
+#define FN(N_, D_) { static bool s_ = false; if (!s_) { set_smem(k_swf_a<N_, D_>, smem); s_ = true; } k_swf_a<N_, D_><<<(unsigned)dm.E, thr, smem, st>>>(r, mul, t1, ghost, dm.fdmS, dm.fdmSt, dm.fdmDinv, zint, ZF); }
+  TP_SWITCH_N(dm.n * 10 + dm.ndim)
+#undef FN
+  ++g_launches; return true;
+}
+bool tp_swf_b(const DevMesh& dm, const double* zint, const double* ZF, const int32_t* t2, const double* ghost, const double* yc, double* out, cudaStream_t st) {
+  const int grid = (int)std::min<size_t>((dm.N2 + 255) / 256, (size_t)148 * 16);
+#define FN(N_, D_) k_swf_b<N_, D_><<<grid, 256, 0, st>>>(zint, ZF, t2, ghost, dm.swt, yc, dm.vertex, dm.w2 + dm.q, out, dm.N2);
+  TP_SWITCH_N(dm.n * 10 + dm.ndim)
+#undef FN
+  ++g_launches; return true;
+}
+void launch_coarse_part_w(const DevMesh& dm, const double* r, const double* mul, double* part, cudaStream_t st) {
+  const int wpb = 8; const unsigned grid = (unsigned)((dm.E + wpb - 1) / wpb);
+  if (dm.ndim == 3) k_coarse_part_w<3><<<grid, 32 * wpb, 0, st>>>(r, mul, part, dm.w2 + dm.q, dm.q, dm.E);
+  else k_coarse_part_w<2><<<grid, 32 * wpb, 0, st>>>(r, mul, part, dm.w2 + dm.q, dm.q, dm.E);
+  ++g_launches;
+}
+void launch_swf_pack(const double* src, const double* mul, const int32_t* idx, int n, double* out, cudaStream_t st) {
+  if (n <= 0) return;
+  k_swf_pack<<<(n + 255) / 256, 256, 0, st>>>(src, mul, idx, n, out); ++g_launches;
 }
 
 }  // namespace nlk

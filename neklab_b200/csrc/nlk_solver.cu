@@ -168,6 +168,26 @@ int apply_precond(nlk_ctx* c, const double* r, double* z, const double* in_mul) 
   }
   // single rank: the coarse branch (restrict -> A0^-1 -> ...) runs on a side stream concurrently with the Schwarz branch
   const bool side = c->have_coarse && c->st2 && c->nccl.nranks <= 1;
+  if (c->swf && c->prm.precond != 3) {                      // fused Schwarz (pull tables): 2 kernels, prolongation folded into the second
+    auto coarse_chain = [&]() -> int {
+      launch_coarse_part_w(dm, r, in_mul, c->crs_part, c->st);
+      launch_vert_gather(dm, c->crs_part, c->crs_r, c->st);
+      if (ctx_allreduce(c, c->crs_r, (int)dm.nvert, false)) return 1;
+      if (c->coarse_sparse) return coarse_solve_sparse(c, c->crs_r, c->crs_y);
+      launch_gemv(dm.A0inv, c->crs_r, c->crs_y, (int)dm.nvert, c->st);
+      return 0;
+    };
+    if (side) {
+      NLK_CUDA(cudaEventRecord(c->ev_in, c->st));
+      NLK_CUDA(cudaStreamWaitEvent(c->st2, c->ev_in, 0));
+      cudaStream_t main_st = c->st; c->st = c->st2;
+      int rc = coarse_chain();
+      c->st = main_st;
+      if (rc) return 1;
+      NLK_CUDA(cudaEventRecord(c->ev_crs, c->st2));
+    } else if (c->have_coarse) { if (coarse_chain()) return 1; }
+    return swf_apply(c, r, in_mul, c->have_coarse ? c->crs_y : nullptr, z, side ? c->ev_crs : nullptr);    // kernel B waits for the coarse solve
+  }
   if (side) {
     NLK_CUDA(cudaEventRecord(c->ev_in, c->st));
     NLK_CUDA(cudaStreamWaitEvent(c->st2, c->ev_in, 0));
@@ -264,7 +284,6 @@ int helmholtz_solve_multi(nlk_ctx* c, int nf, double* const* rhs, double h1, dou
     if (launch_cg_persistent(dm, a, c->st)) return 0;
     c->use_cgp = false;                       // cooperative launch unavailable: fall back for good
   }
-  if (cg3_enabled() && nf > 1 && c->nccl.nranks <= 1) return helmholtz_solve3(c, nf, rhs, h1, h2, masks, tol, sol);   // opt-in prototype (nlk_cg3.cu)
   for (int k = 0; k < nf; ++k) {
     if (helmholtz_solve(c, rhs[k], h1, h2, masks[k], tol, c->cg_x, nullptr)) return 1;
     launch_lin(sol[k], dm.N1, 1.0, sol[k], 1.0, c->cg_x, 0, nullptr, 0, nullptr, nullptr, c->st);

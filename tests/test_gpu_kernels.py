@@ -144,3 +144,28 @@ def test_sparse_coarse_level(nlk_lib):
         assert rel(x4, x1) < 1e-7
         assert it4 <= 3 * it1 + 20, (it1, it4)       # inexact (40-iteration) coarse solves cost outer iterations, not accuracy
         c1.close(); c4.close()
+
+
+@pytest.mark.parametrize("name", ["box2d_n6", "box3d_n5", "box3d_n8_per"])
+def test_fused_schwarz_equals_chain(nlk_lib, name):
+    """The fused Schwarz branch (pull tables, two kernels: nlk_schwarz.cu) against the unfused chain embed -> dssum -> fdm ->
+    dssum -> gather (NLK_NO_SWF=1): same preconditioner to round-off, with and without the left scaling `in_mul`."""
+    import os
+    from neklab_b200 import api
+    om, _, _ = box_case(**CASES[name])
+    m = nlk_mesh(om)
+    r = np.random.default_rng(13).standard_normal(om.bm2.shape)
+    z = {}
+    for key in ("fused", "chain"):
+        if key == "chain":
+            os.environ["NLK_NO_SWF"] = "1"
+        try:
+            ctx = api.Context(m, api.default_params(viscosity=0.02, gmres_maxit=600))
+        finally:
+            os.environ.pop("NLK_NO_SWF", None)
+        u = [om.vmask[c] * x for c, x in enumerate(smooth_fields(om, om.ndim, 10))]
+        rhs = ops.ortho(om, -ops.opdiv(om, u))
+        z[key] = (ctx.precond(r), ctx.pressure(rhs, 1e-10))
+        ctx.close()
+    assert rel(z["fused"][0], z["chain"][0]) < 1e-12, name
+    assert rel(z["fused"][1][0], z["chain"][1][0]) < 1e-8 and abs(z["fused"][1][1] - z["chain"][1][1]) <= 1
