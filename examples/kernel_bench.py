@@ -12,7 +12,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from neklab_b200 import api, build  # noqa: E402
 
-NAMES = {0: "axhelm (K1)", 1: "dssum (K2)", 2: "cdabdtp = opgradt+gs+opdiv (K6)", 3: "convect x d fields (K3)", 4: "precond Schwarz (K10)", 5: "vec dot (K12)", 6: "coarse solve, sparse PCG (K11)", 7: "Schwarz branch alone (K10)"}
+NAMES = {0: "axhelm (K1)", 1: "dssum (K2)", 2: "cdabdtp = opgradt+gs+opdiv (K6)", 3: "convect x d fields (K3)", 4: "precond Schwarz (K10)", 5: "vec dot (K12)", 6: "coarse solve, sparse PCG (K11)", 7: "Schwarz branch alone (K10)", 8: "fused Helmholtz apply of the PCG (K1/K8)", 9: "PCG update+reduce (K8)",
+         10: "opgradt (K5)", 11: "opdiv, fused load scaling (K5)", 12: "dssum x 3 fields (K2)"}
 
 
 def main():

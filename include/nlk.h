@@ -171,6 +171,14 @@ int nlk_exptA_set_tau(nlk_op* op, double tau);                        /* apply_e
 int nlk_exptA_matvec(nlk_op* op, const nlk_vec* in, nlk_vec* out);
 int nlk_exptA_rmatvec(nlk_op* op, const nlk_vec* in, nlk_vec* out);
 int nlk_exptA_stats(const nlk_op* op, nlk_stats* out);
+/* exptA_proj_linop (src/linops/neklab_linops.f90:130-152; exponential_propagator_proj.f90): exptA with a projection of the
+ * velocity onto the streamwise wavenumber alpha, u <- cos(alpha x) <2 u cos(alpha x)> + sin(alpha x) <2 u sin(alpha x)>
+ * (`proj_alpha` :135-173; <.> = Nek `planar_avg`, the bm1-weighted average over the points that share their transverse
+ * coordinates), applied to the initial condition and to the state at tau in matvec AND rmatvec (:46-47, :64-65).
+ * idir = 1, 2, 3 is the averaged direction (the reference's gtpp_gs_setup idir); idir = 0 switches the projection off.
+ * Single rank only.  nlk_exptA_apply_projection applies `proj_alpha` to a vector (self%proj on the solver state). */
+int nlk_exptA_set_projection(nlk_op* op, double alpha, int32_t idir);
+int nlk_exptA_apply_projection(nlk_op* op, nlk_vec* v);
 /* bench hook: start from `in` (history reset as at the top of exptA_matvec), run nwarm untimed + nsteps timed perturbation
  * time steps (body of the loop at exponential_propagator.f90:39-46) and return the device time of the timed ones */
 int nlk_exptA_time_steps(nlk_op* op, const nlk_vec* in, int32_t nwarm, int32_t nsteps, double* ms_timed);

@@ -56,7 +56,7 @@ nlk_mesh_field nlk_mesh_neighbor nlk_mesh_basis nlk_dense_eig nlk_params_default
 nlk_ctx_set_dt nlk_comm_unique_id nlk_ctx_comm_init nlk_ctx_sync nlk_ctx_stream nlk_vec_create nlk_vec_destroy nlk_vec_copy nlk_vec_zero
 nlk_vec_rand nlk_vec_scal nlk_vec_axpby nlk_vec_dot nlk_vec_norm nlk_vec_size nlk_vec_save_rst nlk_vec_get_rst nlk_vec_nrst
 nlk_vec_clear_rst nlk_vec_upload nlk_vec_download nlk_zvec_scal nlk_zvec_axpby nlk_zvec_dot nlk_basis_innerprod nlk_basis_axpy nlk_basis_dgs nlk_exptA_create
-nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_exptA_time_steps nlk_exptA_set_baseflow nlk_nonlinear_map nlk_newton_fixed_point nlk_ctx_set_forcing nlk_set_neklab_forcing nlk_get_neklab_forcing nlk_zero_neklab_forcing nlk_zero_neklab_forcing_ipert nlk_nek2vec nlk_vec2nek
+nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_exptA_time_steps nlk_exptA_set_baseflow nlk_exptA_set_projection nlk_exptA_apply_projection nlk_nonlinear_map nlk_newton_fixed_point nlk_ctx_set_forcing nlk_set_neklab_forcing nlk_get_neklab_forcing nlk_zero_neklab_forcing nlk_zero_neklab_forcing_ipert nlk_nek2vec nlk_vec2nek
 nlk_eigs nlk_svds nlk_gmres nlk_test_axhelm nlk_test_dssum nlk_test_opdiv nlk_test_opgradt nlk_test_cdabdtp nlk_test_convect
 nlk_test_convect_adj nlk_test_helmholtz nlk_test_pressure nlk_test_precond nlk_test_cfl nlk_bench_kernel""".split()
 
@@ -446,6 +446,13 @@ class exptA_linop:
         ms = C.c_double()
         _chk(lib().nlk_exptA_time_steps(self.h, vec_in.h, C.c_int32(nwarm), C.c_int32(nsteps), C.byref(ms)))
         return ms.value
+
+    def set_projection(self, alpha, idir=1):
+        """turn this operator into `exptA_proj_linop(tau, baseflow, alpha)` (src/linops/neklab_linops.f90:130-152); idir = 0: off."""
+        _chk(lib().nlk_exptA_set_projection(self.h, C.c_double(alpha), C.c_int32(idir)))
+
+    def proj(self, vec):
+        _chk(lib().nlk_exptA_apply_projection(self.h, vec.h)); return vec
 
     def stats(self):
         s = Stats(); _chk(lib().nlk_exptA_stats(self.h, C.byref(s)))

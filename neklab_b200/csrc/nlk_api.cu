@@ -562,6 +562,13 @@ static int state_from_vec(nlk_ctx* c, const double* const v[3], const double* pr
   return copy_fields(c, c->vp, c->prp, c->tp, v, pr, th);
 }
 
+// exptA_proj_linop%proj (exponential_propagator_proj.f90:135-173) on d velocity fields
+int exptA_project(nlk_op* op, double* const v[3]) {
+  nlk_ctx* c = op->c; const DevMesh& dm = c->dm;
+  for (int k = 0; k < dm.ndim; ++k)
+    launch_planar_proj(v[k], dm.bm1, op->proj_cv, op->proj_sv, op->proj_off, op->proj_idx, op->proj_gid, op->proj_ngroups, dm.N1, op->proj_coef, c->st);
+  return 0;
+}
 // exptA_matvec / exptA_rmatvec (src/linops/exponential_propagator.f90:15-107) incl. get_rst / compute_rst (:109-142)
 int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose) {
   nlk_ctx* c = op->c;
@@ -574,6 +581,7 @@ int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose) {
   if (push_baseflow(op)) return 1;
   if (step_setup(c, op->tau, transpose)) return 1;
   if (state_from_vec(c, in->v, in->pr, in->theta)) return 1;
+  if (op->proj_dir && exptA_project(op, c->vp)) return 1;                               // exptA_proj: project out unwanted wavenumbers (:46-47)
   if (c->prm.step_variant & 4) NLK_CUDA(cudaMemsetAsync(c->prp, 0, c->dm.N2 * sizeof(double), c->st));
   if (reset_history_pub(c)) return 1;
   for (int istep = 1; istep <= c->nsteps; ++istep) {
@@ -583,6 +591,7 @@ int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose) {
       if (state_from_vec(c, in->rv[istep - 1], in->rpr[istep - 1], in->rth[istep - 1])) return 1;
     }
   }
+  if (op->proj_dir && exptA_project(op, c->vp)) return 1;                               // (:64-65)
   if (copy_fields(c, out->v, out->pr, out->theta, c->vp, c->prp, c->tp)) return 1;       // nek2vec (intent(out): nrst reset)
   out->nrst = 0;
   for (int k = 1; k <= nrst; ++k) {
@@ -606,6 +615,35 @@ int nlk_exptA_init(nlk_op* op) { if (push_baseflow(op)) return 1; return step_se
 int nlk_exptA_matvec(nlk_op* op, const nlk_vec* in, nlk_vec* out) { return exptA_apply(op, in, out, false); }
 int nlk_exptA_rmatvec(nlk_op* op, const nlk_vec* in, nlk_vec* out) { return exptA_apply(op, in, out, true); }
 int nlk_exptA_set_baseflow(nlk_op* op, const nlk_vec* bf) { return nlk_vec_copy(op->baseflow, bf); }
+int nlk_exptA_set_projection(nlk_op* op, double alpha, int32_t idir) {
+  nlk_ctx* c = op->c; const HostMesh& hm = c->mesh->hm; const int d = hm.ndim;
+  if (idir == 0) { op->proj_dir = 0; return 0; }
+  if (idir < 1 || idir > d) { set_error("exptA_proj: idir must be 1..ndim (0 = off)"); return 1; }
+  if (hm.nranks > 1) { set_error("exptA_proj_linop is single-rank only"); return 1; }
+  const size_t N1 = (size_t)hm.E * hm.np1; const int ax = idir - 1;
+  // plane groups: points sharing their transverse coordinates (Nek gtpp_gs_setup on a tensor-product box mesh)
+  double ext = 0; for (int k = 0; k < d; ++k) { auto mm = std::minmax_element(hm.xyz[k].begin(), hm.xyz[k].end()); ext = std::max(ext, *mm.second - *mm.first); }
+  const double tol = 1e-8 * (ext > 0 ? ext : 1.0);
+  std::vector<std::array<int64_t, 3>> key(N1);
+  for (size_t i = 0; i < N1; ++i) { int t = 0; key[i] = {0, 0, (int64_t)i}; for (int k = 0; k < d; ++k) if (k != ax) key[i][t++] = (int64_t)std::llround(hm.xyz[k][i] / tol); }
+  std::sort(key.begin(), key.end());
+  std::vector<int32_t> off(1, 0), idx(N1), gid(N1);
+  for (size_t i = 0; i < N1; ++i) {
+    if (i > 0 && (key[i][0] != key[i - 1][0] || key[i][1] != key[i - 1][1])) off.push_back((int32_t)i);
+    idx[i] = (int32_t)key[i][2]; gid[key[i][2]] = (int32_t)off.size() - 1;
+  }
+  off.push_back((int32_t)N1);
+  std::vector<double> cv(N1), sv(N1);
+  for (size_t i = 0; i < N1; ++i) { cv[i] = std::cos(alpha * hm.xyz[ax][i]); sv[i] = std::sin(alpha * hm.xyz[ax][i]); }
+  op->proj_ngroups = (int64_t)off.size() - 1;
+  if (dev_upload(c, &op->proj_off, off) || dev_upload(c, &op->proj_idx, idx) || dev_upload(c, &op->proj_gid, gid) || dev_upload(c, &op->proj_cv, cv) ||
+      dev_upload(c, &op->proj_sv, sv) || dev_alloc(c, &op->proj_coef, (size_t)2 * op->proj_ngroups)) return 1;
+  op->proj_dir = idir; op->proj_alpha = alpha; return 0;
+}
+int nlk_exptA_apply_projection(nlk_op* op, nlk_vec* v) {
+  if (!op->proj_dir) { set_error("exptA_proj: no projection set"); return 1; }
+  return exptA_project(op, v->v);
+}
 int nlk_nek2vec(nlk_ctx* c, nlk_vec* out) { if (copy_fields(c, out->v, out->pr, out->theta, c->vp, c->prp, c->tp)) return 1; out->nrst = 0; return 0; }
 int nlk_vec2nek(nlk_ctx* c, const nlk_vec* in) { return state_from_vec(c, in->v, in->pr, in->theta); }
 

@@ -144,6 +144,9 @@ struct nlk_op {
   double tau = 1.0;
   nlk_vec* baseflow = nullptr;           // owned copy
   nlk_stats stats{};
+  // exptA_proj_linop: planar-average projection onto one streamwise wavenumber
+  int proj_dir = 0; double proj_alpha = 0; int64_t proj_ngroups = 0;
+  int32_t *proj_off = nullptr, *proj_idx = nullptr, *proj_gid = nullptr; double *proj_cv = nullptr, *proj_sv = nullptr, *proj_coef = nullptr;
 };
 
 namespace nlk {
@@ -153,6 +156,7 @@ int ctx_allreduce(nlk_ctx* c, double* d_ptr, int count, bool maxop);
 int ctx_read_scalars(nlk_ctx* c, int count);                              // d_red[0..count) -> h_red, synchronises
 int vec_alloc_rst(nlk_vec* v, int slot);
 int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose);
+int exptA_project(nlk_op* op, double* const v[3]);
 int step_setup(nlk_ctx* c, double tau, bool transpose);
 int step_setup_cfl(nlk_ctx* c, double tau, double cfl_limit, CPtr3 u);
 int step_advance(nlk_ctx* c, int istep);

@@ -163,6 +163,9 @@ bool tp_swf_b(const DevMesh& dm, const double* zint, const double* ZF, const int
 void launch_coarse_part_w(const DevMesh& dm, const double* r, const double* mul, double* part, cudaStream_t st);
 void launch_swf_pack(const double* src, const double* mul, const int32_t* idx, int n, double* out, cudaStream_t st);
 void launch_vert_gather(const DevMesh& dm, const double* part, double* rc, cudaStream_t st);
+// exptA_proj_linop `proj_alpha`: per plane group, a_c = <2 u cv>, a_s = <2 u sv> (bm1-weighted); then u = cv a_c + sv a_s
+void launch_planar_proj(double* u, const double* bm1, const double* cv, const double* sv, const int32_t* off, const int32_t* idx, const int32_t* gid,
+                        int64_t ngroups, size_t N1, double* coef, cudaStream_t st);
 bool tp_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double alpha, int accumulate, cudaStream_t st);
 bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha, int accumulate, cudaStream_t st, int nj);
 extern thread_local long g_launches;   // counts kernel launches issued through these wrappers

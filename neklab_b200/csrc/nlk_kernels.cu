@@ -2,6 +2,7 @@
 // All kernels are HBM/latency-bound integer+FP64 streaming or small tensor contractions: no tensor cores.
 // Element data is staged in shared memory; 1-D operator matrices are staged in shared memory per CTA.
 #include "nlk_device.cuh"
+#include <cstdlib>
 
 namespace nlk {
 
@@ -217,12 +218,160 @@ k_axhelm(const double* __restrict__ u, double* __restrict__ pio, const double* _
   }
 }
 
+// lx1 = 8, 3-D: the same kernel with the six geometric factors of the element staged through shared memory by cp.async
+// (LDGSTS), one commit group per k-slice, all issued before the first contraction.  ncu r02 on k_axhelm<8,3,1>: 59 % of the
+// samples stalled on the long scoreboard, DRAM at 51 % -- the register prefetch of ONE slice ahead keeps ~49 KB per SM in
+// flight, at the edge of what the HBM latency-bandwidth product needs, and the 64-register cap spilled.  Here ~300 KB per SM
+// are in flight from the first instruction on and the k-loop never waits on global memory again.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_le(int pending) {      // wait until at most `pending` groups are in flight
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+  }
+}
+template <bool FUSE_CG>
+__global__ void __launch_bounds__(128, 4)
+k_axhelm8a(const double* __restrict__ u, double* __restrict__ pio, const double* __restrict__ r, double* __restrict__ w,
+           const double* __restrict__ G, const double* __restrict__ bm1, const double* __restrict__ Dg,
+           const double* __restrict__ hd, double h1, double h2,
+           SolverScal* __restrict__ sc, int64_t E, double* __restrict__ pap_partial, unsigned int* pap_counter, int defer) {
+  constexpr int N = 8, NZ = 8, NN = 64, NP = 512, NG = 6, EPB = 2;
+  extern __shared__ __align__(16) double sG[];              // [EPB][NG][NP]
+  __shared__ double sD[NN], sDt[NN];
+  __shared__ double s_u[EPB][NN], s_gr[EPB][NN], s_gs[EPB][NN];
+  if (FUSE_CG && sc->done) return;
+  const int tid = threadIdx.x, le = threadIdx.y;
+  const int64_t e = (int64_t)blockIdx.x * EPB + le;
+  const int i = tid % N, j = tid / N;
+  const bool active = e < E;
+  const size_t eb = (size_t)(active ? e : 0) * NP;
+  // ---- stage the geometric factors: slice k = 6 arrays x 64 doubles = 192 sixteen-byte chunks, 3 per thread
+  {
+    const double* Ge = G + (size_t)(active ? e : 0) * NG * NP;
+    double* sGe = sG + (size_t)le * NG * NP;
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) {
+#pragma unroll
+      for (int c3 = 0; c3 < 3; ++c3) {
+        const int chunk = tid + NN * c3, a = chunk >> 5, off = a * NP + k * NN + (chunk & 31) * 2;
+        cp_async16(sGe + off, Ge + off);
+      }
+      cp_async_commit();
+    }
+  }
+  for (int idx = tid + le * NN; idx < NN; idx += NN * EPB) { double v = Dg[idx]; sD[idx] = v; sDt[(idx % N) * N + idx / N] = v; }
+  double ru[NZ], rw[NZ], bmv[NZ];
+  if (FUSE_CG) {
+    const double beta = sc->beta;
+    double rv[NZ], hv[NZ], pv[NZ];
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) { const size_t g = eb + k * NN + tid; rv[k] = r[g]; hv[k] = hd[g]; pv[k] = pio[g]; }
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) bmv[k] = bm1[eb + k * NN + tid];
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) {
+      const double p_ = rv[k] * hv[k] + beta * pv[k];       // hd = mask / (h1 diagA + h2 diagB), precomputed per (h1, h2) (k_cg_weights)
+      ru[k] = active ? p_ : 0.0;
+      if (active) pio[eb + k * NN + tid] = p_;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) { ru[k] = active ? u[eb + k * NN + tid] : 0.0; bmv[k] = bm1[eb + k * NN + tid]; }
+  }
+#pragma unroll
+  for (int k = 0; k < NZ; ++k) rw[k] = 0.0;
+  const double* sGe = sG + (size_t)le * NG * NP + tid;
+#pragma unroll
+  for (int k = 0; k < NZ; ++k) {
+    s_u[le][tid] = ru[k];
+    cp_async_wait_le(NZ - 1 - k);
+    __syncthreads();
+    double gc[NG];
+#pragma unroll
+    for (int c = 0; c < NG; ++c) gc[c] = sGe[c * NP + k * NN];
+    double ur = 0, us = 0, ut = 0;
+#pragma unroll
+    for (int l = 0; l < N; ++l) {
+      ur += sDt[l * N + i] * s_u[le][j * N + l];
+      us += sD[j * N + l] * s_u[le][l * N + i];
+    }
+#pragma unroll
+    for (int l = 0; l < N; ++l) ut += c_D[k * N + l] * ru[l];
+    const double gr = gc[0] * ur + gc[3] * us + gc[4] * ut;
+    const double gs = gc[3] * ur + gc[1] * us + gc[5] * ut;
+    const double gt = gc[4] * ur + gc[5] * us + gc[2] * ut;
+    s_gr[le][tid] = gr; s_gs[le][tid] = gs;
+    __syncthreads();
+    double acc = 0;
+#pragma unroll
+    for (int l = 0; l < N; ++l) acc += sD[l * N + i] * s_gr[le][j * N + l] + sD[l * N + j] * s_gs[le][l * N + i];
+    rw[k] += acc;
+#pragma unroll
+    for (int l = 0; l < N; ++l) rw[l] += c_D[k * N + l] * gt;
+    __syncthreads();
+  }
+  double pap = 0.0;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) { const size_t g = eb + k * NN + tid; const double wv = h1 * rw[k] + h2 * bmv[k] * ru[k]; w[g] = wv; if (FUSE_CG) pap += ru[k] * wv; }
+  }
+  if (FUSE_CG) {
+    constexpr int NT = NN * EPB;
+    double* sred = &s_gr[0][0];                     // free after the last barrier of the k-loop
+    __shared__ int s_last;
+    const int lt = le * NN + tid;
+    sred[lt] = pap;
+    __syncthreads();
+    if (lt < 32) { double t = 0; for (int q = lt; q < NT; q += 32) t += sred[q]; sred[lt] = t; }
+    __syncthreads();
+    if (lt == 0) {
+      double t = 0; for (int q = 0; q < 32; ++q) t += sred[q];
+      pap_partial[blockIdx.x] = t; __threadfence();
+      s_last = (atomicAdd(pap_counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      double t = 0; for (unsigned b = lt; b < gridDim.x; b += NT) t += __ldcg(&pap_partial[b]);
+      sred[lt] = t;
+      __syncthreads();
+      if (lt == 0) {
+        double tt = 0; for (int q = 0; q < NT; ++q) tt += sred[q];
+        sc->red[2] = tt; if (!defer) cg_finalize_pap(sc);
+        *pap_counter = 0u;
+      }
+    }
+  }
+}
+
 template <int N, int DIM>
 static void axhelm_dispatch(const DevMesh& dm, const double* u, double* pio, const double* r, double* w, const double* hd, double h1, double h2,
                             SolverScal* sc, bool fuse, double* pap_partial, unsigned int* pap_counter, int defer, cudaStream_t st) {
   constexpr int EPB = N * N >= 100 ? 1 : (N * N >= 64 ? 2 : 4);
   ensure_const_D(dm, st);
   dim3 block(N * N, EPB), grid(cdiv(dm.E, EPB));
+  if constexpr (N == 8 && DIM == 3) {
+    static const bool no_async = getenv("NLK_NO_AXASYNC") != nullptr;
+    if (!no_async) {
+      constexpr size_t smem = (size_t)EPB * 6 * 512 * sizeof(double);
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(k_axhelm8a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaFuncSetAttribute(k_axhelm8a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+      if (fuse) k_axhelm8a<true><<<grid, block, smem, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, hd, h1, h2, sc, dm.E, pap_partial, pap_counter, defer);
+      else k_axhelm8a<false><<<grid, block, smem, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, nullptr, h1, h2, nullptr, dm.E, nullptr, nullptr, 0);
+      LAUNCH_COUNT(); return;
+    }
+  }
   if (fuse) k_axhelm<N, DIM, true><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, hd, h1, h2, sc, dm.E, pap_partial, pap_counter, defer);
   else k_axhelm<N, DIM, false><<<grid, block, 0, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, nullptr, h1, h2, nullptr, dm.E, nullptr, nullptr, 0);
   LAUNCH_COUNT();
@@ -251,20 +400,47 @@ void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, 
 }
 
 // ------------------------------------------------------------------------------------------------ K2 dssum
-__global__ void k_gs(Ptr3 f, int nf, const int32_t* __restrict__ off, const int32_t* __restrict__ idx, int ngs) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per shared global node.  Groups of 2 (face-interior nodes: three quarters of all groups) and 4 (edge-interior nodes
+// of a conforming hex mesh) are handled with all index loads, then all value loads, issued together -- the generic loop chains
+// two dependent loads per copy.  Copies are always summed in ascending local order (deterministic, identical on every copy).
+template <int NF>
+__global__ void k_gs(Ptr3 f, const int32_t* __restrict__ off, const int32_t* __restrict__ idx, int ngs) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ngs) return;
-  const int b = off[g], e = off[g + 1];
-  for (int c = 0; c < nf; ++c) {
-    double* u = f.p[c];
-    double s = 0;
-    for (int t = b; t < e; ++t) s += u[idx[t]];
-    for (int t = b; t < e; ++t) u[idx[t]] = s;
+  const int b = off[g], n = off[g + 1] - b;
+  double* const u0 = f.p[0]; double* const u1 = NF > 1 ? f.p[1] : nullptr; double* const u2 = NF > 2 ? f.p[2] : nullptr;
+  if (n == 2) {
+    const int i0 = idx[b], i1 = idx[b + 1];
+    double a0 = u0[i0], a1 = u0[i1], b0 = 0, b1 = 0, c0 = 0, c1 = 0;
+    if (NF > 1) { b0 = u1[i0]; b1 = u1[i1]; }
+    if (NF > 2) { c0 = u2[i0]; c1 = u2[i1]; }
+    const double sa = a0 + a1; u0[i0] = sa; u0[i1] = sa;
+    if (NF > 1) { const double sb = b0 + b1; u1[i0] = sb; u1[i1] = sb; }
+    if (NF > 2) { const double sc_ = c0 + c1; u2[i0] = sc_; u2[i1] = sc_; }
+  } else if (n == 4) {
+    const int i0 = idx[b], i1 = idx[b + 1], i2 = idx[b + 2], i3 = idx[b + 3];
+    double a[4] = {u0[i0], u0[i1], u0[i2], u0[i3]}, bb[4] = {0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};
+    if (NF > 1) { bb[0] = u1[i0]; bb[1] = u1[i1]; bb[2] = u1[i2]; bb[3] = u1[i3]; }
+    if (NF > 2) { cc[0] = u2[i0]; cc[1] = u2[i1]; cc[2] = u2[i2]; cc[3] = u2[i3]; }
+    const double sa = ((a[0] + a[1]) + a[2]) + a[3]; u0[i0] = sa; u0[i1] = sa; u0[i2] = sa; u0[i3] = sa;
+    if (NF > 1) { const double sb = ((bb[0] + bb[1]) + bb[2]) + bb[3]; u1[i0] = sb; u1[i1] = sb; u1[i2] = sb; u1[i3] = sb; }
+    if (NF > 2) { const double sc_ = ((cc[0] + cc[1]) + cc[2]) + cc[3]; u2[i0] = sc_; u2[i1] = sc_; u2[i2] = sc_; u2[i3] = sc_; }
+  } else {
+    const int e = b + n;
+#pragma unroll
+    for (int c = 0; c < NF; ++c) {
+      double* u = c == 0 ? u0 : (c == 1 ? u1 : u2);
+      double s = 0;
+      for (int t = b; t < e; ++t) s += u[idx[t]];
+      for (int t = b; t < e; ++t) u[idx[t]] = s;
+    }
   }
 }
 void launch_gs(const DevMesh& dm, Ptr3 f, int nf, cudaStream_t st) {
   if (dm.ngs == 0) return;
-  k_gs<<<cdiv(dm.ngs, 128), 128, 0, st>>>(f, nf, dm.gs_off, dm.gs_idx, dm.ngs);
+  if (nf == 1) k_gs<1><<<cdiv(dm.ngs, 128), 128, 0, st>>>(f, dm.gs_off, dm.gs_idx, dm.ngs);
+  else if (nf == 2) k_gs<2><<<cdiv(dm.ngs, 128), 128, 0, st>>>(f, dm.gs_off, dm.gs_idx, dm.ngs);
+  else k_gs<3><<<cdiv(dm.ngs, 128), 128, 0, st>>>(f, dm.gs_off, dm.gs_idx, dm.ngs);
   LAUNCH_COUNT();
 }
 
@@ -913,6 +1089,26 @@ __global__ void k_vert_gather(const double* __restrict__ part, const int32_t* __
   double s = 0;
   for (int t = off[v]; t < off[v + 1]; ++t) s += part[ec[t]];
   rc[v] = s;
+}
+// one warp per plane group: bm1-weighted averages of 2 u cv and 2 u sv (Nek planar_avg), fixed summation order (deterministic)
+__global__ void k_planar_avg(const double* __restrict__ u, const double* __restrict__ bm1, const double* __restrict__ cv, const double* __restrict__ sv,
+                             const int32_t* __restrict__ off, const int32_t* __restrict__ idx, int64_t ngroups, double* __restrict__ coef) {
+  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= ngroups) return;
+  double sc = 0, ss = 0, sm_ = 0;
+  for (int t = off[g] + lane; t < off[g + 1]; t += 32) { const int p = idx[t]; const double b = bm1[p], ub = 2.0 * u[p] * b; sc += ub * cv[p]; ss += ub * sv[p]; sm_ += b; }
+  sc = warp_sum(sc); ss = warp_sum(ss); sm_ = warp_sum(sm_);
+  if (lane == 0) { coef[2 * g] = sc / sm_; coef[2 * g + 1] = ss / sm_; }
+}
+__global__ void k_planar_apply(double* __restrict__ u, const double* __restrict__ cv, const double* __restrict__ sv, const int32_t* __restrict__ gid,
+                               const double* __restrict__ coef, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { const int g = gid[i]; u[i] = cv[i] * coef[2 * g] + sv[i] * coef[2 * g + 1]; }
+}
+void launch_planar_proj(double* u, const double* bm1, const double* cv, const double* sv, const int32_t* off, const int32_t* idx, const int32_t* gid,
+                        int64_t ngroups, size_t N1, double* coef, cudaStream_t st) {
+  k_planar_avg<<<cdiv((size_t)ngroups, 4), 128, 0, st>>>(u, bm1, cv, sv, off, idx, ngroups, coef); LAUNCH_COUNT();
+  k_planar_apply<<<std::min(cdiv(N1, 256), 148 * 8), 256, 0, st>>>(u, cv, sv, gid, coef, N1); LAUNCH_COUNT();
 }
 void launch_vert_gather(const DevMesh& dm, const double* part, double* rc, cudaStream_t st) {
   k_vert_gather<<<cdiv(dm.nvert, 128), 128, 0, st>>>(part, dm.vert_off, dm.vert_ec, rc, dm.nvert); LAUNCH_COUNT();

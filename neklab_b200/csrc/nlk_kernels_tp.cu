@@ -4,6 +4,8 @@
 // bounded by HBM traffic of the element data rather than by shared-memory bandwidth.  In 2-D (few pencils) one thread
 // per output point with fully unrolled loops is used.  Runtime-sized fallbacks live in nlk_kernels.cu.
 #include "nlk_device.cuh"
+#include "nlk_dmma.cuh"
+#include <cstdlib>
 
 namespace nlk {
 
@@ -84,6 +86,12 @@ __device__ __forceinline__ void contract_t(double* __restrict__ out, const doubl
   }
   __syncthreads();
 }
+// pointer selects instead of dynamic indexing into by-value pointer structs (which the compiler spills to local memory and then
+// reads with generic LD.E loads)
+__device__ __forceinline__ const double* sel3(const CPtr3& a, int c) { return c == 0 ? a.p[0] : (c == 1 ? a.p[1] : a.p[2]); }
+__device__ __forceinline__ double* sel3(const Ptr3& a, int c) { return c == 0 ? a.p[0] : (c == 1 ? a.p[1] : a.p[2]); }
+__device__ __forceinline__ const double* sel4(const CPtr4& a, int c) { return c == 0 ? a.p[0] : (c == 1 ? a.p[1] : (c == 2 ? a.p[2] : a.p[3])); }
+__device__ __forceinline__ double* sel4(const Ptr4& a, int c) { return c == 0 ? a.p[0] : (c == 1 ? a.p[1] : (c == 2 ? a.p[2] : a.p[3])); }
 __device__ __forceinline__ void load_mat_t(double* s, const double* g, int cnt) {
   for (int i = threadIdx.x; i < cnt; i += blockDim.x) s[i] = g[i];
 }
@@ -230,8 +238,8 @@ k_opdiv3_t(CPtr3 u, double* __restrict__ p, const double* __restrict__ rxw2, dou
   const double* rw = rxw2 + e * (size_t)9 * np2;
   if (e + PF_DIST < gridDim.x) {
     const size_t en = e + PF_DIST;
-    prefetch_l2(u.p[c] + en * np1, np1, t, P);
-    if (in_mul) { prefetch_l2(in_mask.p[c] + en * np1, np1, t, P); if (c == 0) prefetch_l2(in_mul + en * np1, np1, t, P); }
+    prefetch_l2((c == 0 ? u.p[0] : (c == 1 ? u.p[1] : u.p[2])) + en * np1, np1, t, P);
+    if (in_mul) { prefetch_l2((c == 0 ? in_mask.p[0] : (c == 1 ? in_mask.p[1] : in_mask.p[2])) + en * np1, np1, t, P); if (c == 0) prefetch_l2(in_mul + en * np1, np1, t, P); }
     prefetch_l2(rxw2 + en * (size_t)9 * np2 + (size_t)c * 3 * np2, 3 * np2, t, P);
   }
   // metrics for the z stage, fetched first (consumed last)
@@ -241,9 +249,23 @@ k_opdiv3_t(CPtr3 u, double* __restrict__ p, const double* __restrict__ rxw2, dou
     for (int a = 0; a < q; ++a) { const int g = a * q * q + t; m0[a] = rw[(0 * 3 + c) * np2 + g]; m1[a] = rw[(1 * 3 + c) * np2 + g]; m2[a] = rw[(2 * 3 + c) * np2 + g]; }
   }
   {
-    const double* uc = u.p[c] + e * np1;
-    if (in_mul) { const double* mk = in_mask.p[c] + e * np1; const double* bi = in_mul + e * np1; for (int i = t; i < np1; i += P) U[(i / n) * npad + (i % n)] = uc[i] * bi[i] * mk[i]; }
-    else for (int i = t; i < np1; i += P) U[(i / n) * npad + (i % n)] = uc[i];
+    // all loads of the element are issued before the first use (ncu r02: the rolled loop `load, load, multiply, store` exposed one
+    // DRAM latency per trip -- 53 % of the samples stalled on the long scoreboard at that multiply)
+    constexpr int NI = (np1 + P - 1) / P;
+    const double* __restrict__ uc = (c == 0 ? u.p[0] : (c == 1 ? u.p[1] : u.p[2])) + e * np1;
+    double uv[NI];
+#pragma unroll
+    for (int q_ = 0; q_ < NI; ++q_) { const int i = t + q_ * P; uv[q_] = i < np1 ? __ldg(uc + i) : 0.0; }
+    if (in_mul) {
+      const double* __restrict__ mk = (c == 0 ? in_mask.p[0] : (c == 1 ? in_mask.p[1] : in_mask.p[2])) + e * np1; const double* __restrict__ bi = in_mul + e * np1;
+      double bv[NI], mv[NI];
+#pragma unroll
+      for (int q_ = 0; q_ < NI; ++q_) { const int i = t + q_ * P; bv[q_] = i < np1 ? __ldg(bi + i) : 0.0; mv[q_] = i < np1 ? __ldg(mk + i) : 0.0; }
+#pragma unroll
+      for (int q_ = 0; q_ < NI; ++q_) uv[q_] *= bv[q_] * mv[q_];
+    }
+#pragma unroll
+    for (int q_ = 0; q_ < NI; ++q_) { const int i = t + q_ * P; if (i < np1) U[(i / n) * npad + (i % n)] = uv[q_]; }
   }
   group_sync(c + 1, P);
   // ---- x stage: A = D12_x u, B = I12_x u
@@ -329,10 +351,25 @@ k_opgradt3_t(const double* __restrict__ p, Ptr3 w, const double* __restrict__ rx
     if (c == 0) prefetch_l2(p + en * np2, np2, t, P);
     prefetch_l2(rxw2 + en * (size_t)9 * np2 + (size_t)c * 3 * np2, 3 * np2, t, P);
   }
-  // S_k = p * rxw2[k][c], k = 0..2, coalesced into padded tiles
-  for (int i = t; i < 3 * np2; i += P) {
-    const int k = i / np2, r_ = i - k * np2;
-    S[k * qp * q * q + (r_ / q) * qp + (r_ % q)] = pe[r_] * rw[(size_t)(k * 3 + c) * np2 + r_];
+  // S_k = p * rxw2[k][c], k = 0..2, coalesced into padded tiles; every load issued before the first use (see k_opdiv3_t)
+  {
+    constexpr int NI = (np2 + P - 1) / P;
+    double pv[NI], rv[3][NI];
+#pragma unroll
+    for (int q_ = 0; q_ < NI; ++q_) {
+      const int r_ = t + q_ * P;
+      pv[q_] = r_ < np2 ? __ldg(pe + r_) : 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) rv[k][q_] = r_ < np2 ? __ldg(rw + (size_t)(k * 3 + c) * np2 + r_) : 0.0;
+    }
+#pragma unroll
+    for (int q_ = 0; q_ < NI; ++q_) {
+      const int r_ = t + q_ * P;
+      if (r_ < np2) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) S[k * qp * q * q + (r_ / q) * qp + (r_ % q)] = pv[q_] * rv[k][q_];
+      }
+    }
   }
   group_sync(c + 1, P);
   // ---- x stage: A0 = D12^T_x S0, A1 = I12^T_x S1, A2 = I12^T_x S2       pencils (jq,kq)
@@ -383,7 +420,7 @@ k_opgradt3_t(const double* __restrict__ p, Ptr3 w, const double* __restrict__ rx
 #pragma unroll
     for (int l = 0; l < q; ++l) r[l] = B1[t + n * n * l];
     pen_apply<n, q, MAT_D12T>(r, o);
-    double* wc = w.p[c] + e * np1;
+    double* wc = (c == 0 ? w.p[0] : (c == 1 ? w.p[1] : w.p[2])) + e * np1;
 #pragma unroll
     for (int a = 0; a < n; ++a) wc[t + n * n * a] = o[a];
   }
@@ -415,13 +452,13 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
 #pragma unroll
     for (int q = 0; q < PRE; ++q) { const int i = threadIdx.x + q * NT; if (i < np1) W1[(i % n) + PN * (i / n)] = pre[q]; }
   };
-  if constexpr (DIM == 3) fetch(C.p[0] + e * np1);
+  if constexpr (DIM == 3) fetch(sel3(C, 0) + e * np1);
   load_mat_t(sI, I1dg, m * n); load_mat_t(sIt, I1dtg, m * n); load_mat_t(sDd, Ddg, m * m);
   __syncthreads();
 #pragma unroll 1
   for (int c = 0; c < d; ++c) {
     if constexpr (DIM == 2) {
-      const double* cc = C.p[c] + e * np1;
+      const double* cc = sel3(C, c) + e * np1;
       for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = cc[i];
       __syncthreads();
       contract_t<m, n, 0, false, n, n, 1, MAT_I1D>(W2, W1, sI);
@@ -429,7 +466,7 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
     } else {
       stage();
       __syncthreads();
-      fetch((c + 1 < d ? C.p[c + 1] : u.p[0]) + e * np1);
+      fetch((c + 1 < d ? sel3(C, c + 1) : sel4(u, 0)) + e * np1);
       contract_t<m, n, 0, false, n, n, n, MAT_I1D, PN, PM>(W2, W1, sI);
       contract_t<m, n, 1, false, m, n, n, MAT_I1D, PM, PM>(W1, W2, sI);
       contract_t<m, n, 2, false, m, m, n, MAT_I1D, PM, PM>(TR + c * npdP, W1, sI);
@@ -452,11 +489,11 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
 #pragma unroll 1
   for (int f = 0; f < nf; ++f) {
     if constexpr (DIM == 2) {
-      const double* uf = u.p[f] + e * np1;
+      const double* uf = sel4(u, f) + e * np1;
       for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[i] = uf[i];
     } else {
       stage();
-      if (f + 1 < nf) fetch(u.p[f + 1] + e * np1);
+      if (f + 1 < nf) fetch(sel4(u, f + 1) + e * np1);
     }
     __syncthreads();
     if constexpr (DIM == 2) {
@@ -487,7 +524,7 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
       contract_t<n, m, 1, false, n, m, m, MAT_I1DT, PN, PN>(UF, W1, sIt);
       contract_t<n, m, 2, false, n, n, m, MAT_I1DT, PN, PN>(W2, UF, sIt);
     }
-    double* of = out.p[f] + e * np1;
+    double* of = sel4(out, f) + e * np1;
     for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[(i % n) + PN * (i / n)];
     __syncthreads();
   }
@@ -512,7 +549,7 @@ __global__ void k_convect_adj_t(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __res
   for (int j = 0; j < nj; ++j) {
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-      const double* src = (pass == 0 ? cf.p[j] : U.p[j]) + e * np1;
+      const double* src = (pass == 0 ? sel3(cf, j) : sel3(U, j)) + e * np1;
       double* dst = pass == 0 ? CF : UF;
       for (int i = threadIdx.x; i < np1; i += blockDim.x) W1[(i % n) + PN * (i / n)] = src[i];
       __syncthreads();
@@ -545,7 +582,7 @@ __global__ void k_convect_adj_t(CPtr3 U, CPtr3 cf, Ptr3 out, const double* __res
       contract_t<n, m, 1, false, n, m, m, MAT_I1DT, PN, PN>(UF, W1, sIt);
       contract_t<n, m, 2, false, n, n, m, MAT_I1DT, PN, PN>(W2, UF, sIt);
     }
-    double* of = out.p[c] + e * np1;
+    double* of = sel3(out, c) + e * np1;
     for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[(i % n) + PN * (i / n)];
     __syncthreads();
   }
@@ -700,6 +737,76 @@ __global__ void k_swf_b(const double* __restrict__ zint, const double* __restric
     out[g] = v;
   }
 }
+// ---- FP64 tensor-core (DMMA) version of kernel A for lx1 = 8 in 3-D: one WARP per element.
+// The six contractions of the FDM solve are (8 x 8) x (8 x 64) products.  With scalar FMAs every one of the 24.6 k FMAs of an
+// element needs its own shared-memory operand (the S matrices differ from element to element, so the constant-bank trick of
+// the fixed-operator kernels does not apply): ncu r01/r02 show the LSU pipe, not DRAM or the FP64 pipe, as the limiter
+// (168 registers, 18 % of the warps active).  mma.sync.m8n8k4.f64 takes the operator as a 2-register A fragment held for a
+// whole contraction and the data as one 8-byte shared-memory load per lane and 256 FMAs: 16 DMMA + 16 LDS + 16 STS per
+// contraction and warp instead of ~1 000 LDS.  FP64 has no tcgen05 path; DMMA is the FP64 tensor pipe of sm_100a.
+constexpr int SWF8_WARPS = 4;
+__global__ void __launch_bounds__(32 * SWF8_WARPS)
+k_swf_a8(const double* __restrict__ r, const double* __restrict__ mul, const int32_t* __restrict__ t1, const double* __restrict__ ghost,
+         const double* __restrict__ S, const double* __restrict__ St, const double* __restrict__ dinv,
+         double* __restrict__ zint, double* __restrict__ ZF, int64_t E) {
+  constexpr int n = 8, q = 6, np1 = 512, nn = 64, np2 = 216, NF = 6, FS = 36, PN = 9, npP = PN * 64;
+  __shared__ double tiles[SWF8_WARPS][2][npP];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t e = (int64_t)blockIdx.x * SWF8_WARPS + w;
+  if (e >= E) return;
+  double* A = tiles[w][0]; double* B = tiles[w][1];
+  // operator fragments: A-fragment of M is M[lane>>2][kb*4 + (lane&3)]
+  const double* Se = S + e * (size_t)(3 * nn); const double* Ste = St + e * (size_t)(3 * nn);
+  const int fr = (lane >> 2) * n + (lane & 3);
+  double st0[3], st1[3], s0[3], s1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { st0[k] = Ste[k * nn + fr]; st1[k] = Ste[k * nn + fr + 4]; s0[k] = Se[k * nn + fr]; s1[k] = Se[k * nn + fr + 4]; }
+  const int32_t* te = t1 + e * (size_t)(NF * FS);
+  {
+    // two batched load phases (all 16 index loads, then all 16 value loads) before the first shared-memory store: a rolled loop
+    // exposed two dependent DRAM latencies per trip (ncu r02: 60 % of the samples on the long scoreboard)
+    long long src[16];                       // >= 0: index into r ; -1: zero ; <= -2: ghost slot
+#pragma unroll
+    for (int q_ = 0; q_ < 16; ++q_) {
+      const int p = lane + 32 * q_;
+      const int i = p & 7, j = (p >> 3) & 7, k = p >> 6;
+      int f, s_, nb; swf_face_of<8, 3>(i, j, k, f, s_, nb);
+      src[q_] = -1;
+      if (nb == 0) src[q_] = (long long)(e * np2 + (size_t)((k - 1) * q + (j - 1)) * q + (i - 1));
+      else if (nb == 1) src[q_] = __ldg(te + f * FS + s_);
+    }
+    double v[16], m_[16];
+#pragma unroll
+    for (int q_ = 0; q_ < 16; ++q_) {
+      v[q_] = 0.0; m_[q_] = 1.0;
+      if (src[q_] >= 0) { v[q_] = __ldg(r + src[q_]); if (mul) m_[q_] = __ldg(mul + src[q_]); }
+      else if (src[q_] <= -2) v[q_] = __ldg(ghost + (-2 - src[q_]));
+    }
+#pragma unroll
+    for (int q_ = 0; q_ < 16; ++q_) { const int p = lane + 32 * q_; A[(p & 7) + PN * (p >> 3)] = v[q_] * m_[q_]; }
+  }
+  __syncwarp();
+  double dv[16];                             // inverse eigenvalue sums, fetched now, consumed after the three forward contractions
+#pragma unroll
+  for (int q_ = 0; q_ < 16; ++q_) dv[q_] = __ldg(dinv + e * np1 + lane + 32 * q_);
+  dmma_contract8<0, PN>(B, A, st0[0], st1[0], lane);
+  dmma_contract8<1, PN>(A, B, st0[1], st1[1], lane);
+  dmma_contract8<2, PN>(B, A, st0[2], st1[2], lane);
+#pragma unroll
+  for (int q_ = 0; q_ < 16; ++q_) { const int p = lane + 32 * q_; B[(p & 7) + PN * (p >> 3)] *= dv[q_]; }
+  __syncwarp();
+  dmma_contract8<0, PN>(A, B, s0[0], s1[0], lane);
+  dmma_contract8<1, PN>(B, A, s0[1], s1[1], lane);
+  dmma_contract8<2, PN>(A, B, s0[2], s1[2], lane);
+  for (int p = lane; p < np1; p += 32) {
+    const int i = p & 7, j = (p >> 3) & 7, k = p >> 6;
+    int f, s_, nb; swf_face_of<8, 3>(i, j, k, f, s_, nb);
+    const double v = A[i + PN * (p >> 3)];
+    if (nb == 0) zint[e * np2 + (size_t)((k - 1) * q + (j - 1)) * q + (i - 1)] = v;
+    else if (nb == 1) ZF[e * (size_t)(NF * FS) + f * FS + s_] = v;
+  }
+}
+
 // coarse restriction, one warp per element: part[e][c] = sum_p shape_c(p) r[e][p] (* mul), coalesced
 template <int DIM>
 __global__ void k_coarse_part_w(const double* __restrict__ r, const double* __restrict__ mul, double* __restrict__ part, const double* __restrict__ z2, int q, int64_t E) {
@@ -813,6 +920,11 @@ bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha,
 }
 
 bool tp_swf_a(const DevMesh& dm, const double* r, const double* mul, const int32_t* t1, const double* ghost, double* zint, double* ZF, cudaStream_t st) {
+  static const bool no_dmma = getenv("NLK_NO_DMMA") != nullptr;
+  if (dm.n == 8 && dm.ndim == 3 && !no_dmma) {            // FP64 tensor-core path, one warp per element
+    k_swf_a8<<<(unsigned)((dm.E + SWF8_WARPS - 1) / SWF8_WARPS), 32 * SWF8_WARPS, 0, st>>>(r, mul, t1, ghost, dm.fdmS, dm.fdmSt, dm.fdmDinv, zint, ZF, dm.E);
+    ++g_launches; return true;
+  }
   const size_t npP = dm.ndim == 3 ? (size_t)(dm.n | 1) * dm.n * dm.n : (size_t)dm.np1;
   size_t smem = (size_t)(2 * dm.ndim * dm.n * dm.n + 2 * npP) * sizeof(double);
   int thr = tp_threads(dm.n, dm.ndim, dm.np1);

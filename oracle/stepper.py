@@ -643,3 +643,53 @@ class ExptA:
 
     def rmatvec(self, vec_in):
         return self._apply(vec_in, True)
+
+
+# --------------------------------------------------------------------------- exptA_proj
+class ExptAProj(ExptA):
+    """`exptA_proj_linop` (src/linops/neklab_linops.f90:130-152; exponential_propagator_proj.f90): exptA with the velocity
+    projected onto the streamwise wavenumber alpha before the time loop and at tau (`proj_alpha`, :135-173):
+    u <- cos(alpha x) <2 u cos(alpha x)> + sin(alpha x) <2 u sin(alpha x)>, <.> = Nek `planar_avg` (bm1-weighted average over
+    the points sharing their transverse coordinates)."""
+
+    def __init__(self, stepper, tau, baseflow, alpha, idir=1):
+        super().__init__(stepper, tau, baseflow)
+        m = stepper.mesh
+        ax = idir - 1
+        x = m.coords
+        ext = max(float(np.ptp(x[:, c])) for c in range(m.ndim))
+        keys = np.stack([np.round(x[:, c] / (1e-8 * ext)).astype(np.int64).ravel() for c in range(m.ndim) if c != ax], axis=1)
+        _, self.gid = np.unique(keys, axis=0, return_inverse=True)
+        self.gid = self.gid.ravel()
+        self.cv = np.cos(alpha * x[:, ax]); self.sv = np.sin(alpha * x[:, ax])
+        self.msum = np.bincount(self.gid, weights=m.bm1.ravel())
+
+    def planar_avg(self, u):
+        m = self.st.mesh
+        return (np.bincount(self.gid, weights=(u * m.bm1).ravel()) / self.msum)[self.gid].reshape(u.shape)
+
+    def proj(self, v):
+        return [self.cv * self.planar_avg(2.0 * u * self.cv) + self.sv * self.planar_avg(2.0 * u * self.sv) for u in v]
+
+    def _apply(self, vec_in, transpose):
+        st = self.st
+        nrst = st.prm.torder - 1
+        st.U = [x.copy() for x in self.bf.v]; st.T = self.bf.theta.copy()
+        st.setup(self.tau, 0.5, transpose)
+        st.set_state(self.proj(vec_in.v), vec_in.pr, vec_in.theta)            # :46-47
+        st.reset_history()
+        for istep in range(1, st.nsteps + 1):
+            st.advance(istep)
+            if istep <= nrst and vec_in.nrst > 0:
+                r = vec_in.get_rst(istep)
+                st.set_state(r.v, r.pr, r.theta)
+        st.set_state(self.proj(st.vp), st.prp, st.tp)                         # :64-65
+        out = NekVec(st.mesh, st.prm.torder, st.prm.ifheat)
+        out.v = [x.copy() for x in st.vp]; out.pr = st.prp.copy(); out.theta = st.tp.copy()
+        for k in range(1, nrst + 1):
+            st.advance(st.nsteps + k)
+            s = NekVec(st.mesh, st.prm.torder, st.prm.ifheat)
+            s.v = [x.copy() for x in st.vp]; s.pr = st.prp.copy(); s.theta = st.tp.copy()
+            out.save_rst(s, k)
+        self.nmatvec += 1
+        return out
