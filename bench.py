@@ -229,14 +229,14 @@ def _cpu_value(workload, s):
 def synth_config(a, world):
     L = a.layers_total if a.scaling == "strong" else a.layers * world
     return {"workload": "synth3d_extruded_cylinder_time_step", "elements": 1996 * L, "lx1": 8, "lxd": 12, "layers_total": L,
-            "timestepper": "bdf3", "residualProj": 20, "tolerances": {"velocity": 1e-9, "pressure": 1e-7}}
+            "timestepper": "bdf3", "residualProj": 20, "tolerances": {"velocity": 1e-9, "pressure": 1e-7},
+            "l2": "inputs larger than L2 (state + geometry + dealiasing metrics ~ %.1f GB in total)" % (1996 * L * 512 * 8 * 75 / 1e9)}
 
 
 def reference_arm(workload, steps, warmup, a):
     s = cpu_sample(workload, steps, warmup, a.cpu_window)
     val, unit = _cpu_value(workload, s)
     cfg = synth_config(a, max(a.gpus, 1)) if workload == "synth3d" else {"workload": "cylinder_re50_exptA_matvec", "elements": 1996, "lx1": 6, "lxd": 9, "timestepper": "bdf3", "tau": 1.0, "residualProj": 20}
-    cfg["cpu_sample"] = s["sample"]
     ms = s["sec_per_step"] * 1e3 * (s["steps_per_matvec"] if workload == "cylinder" else 1)
     base = {"value": val, "unit": unit, "cores": s["threads"], "kind": "port", "sample": s["sample"]}
     return {"metric": "exptA matvec/s" if workload == "cylinder" else "GDOF*steps/s", "value": val, "unit": unit, "n_gpus": 0,
@@ -390,8 +390,7 @@ def native_arm(workload, steps, warmup, a, rank, world, local):
         extra = {"time_steps_timed": int(s["steps"]), "spinup_steps": int(spin), "cg_iters_per_step": s["cg_iters"] / steps, "gmres_iters_per_step": s["gmres_iters"] / steps,
                  "launches_per_time_step": launches / steps, "dt": s0["dt"], "points_per_gpu": int(npts), "setup_s": t_setup,
                  "check": {"state_norm_after_timed_steps": state_norm, "note": "global bm1 norm of the perturbation after spinup+steps time steps from the same seeded start vector; equal across N up to solver tolerance"}}
-        cfg.update({"partition": "z-slabs of whole 2-D layers: rank r owns layers [%s)" % ", ".join(str(int(b)) for b in bounds) if world > 1 else "single rank",
-                    "l2": "inputs larger than L2 (state + geometry + dealiasing metrics ~ %.1f GB per GPU)" % (npts * 8 * 75 / 1e9)})
+        extra["partition"] = ("z-slabs of whole 2-D layers, layer bounds %s" % [int(b) for b in bounds]) if world > 1 else "single rank"
         # roofline of the dominant kernel of the step, at this problem size: the fused Helmholtz apply the Jacobi-PCG launches
         # (p = hd r + beta p on load, p.Ap on the way out); CUDA events on the library stream right after the timed region
         ms_ax, bytes_ax = ctx.bench_kernel(8, 50)

@@ -61,6 +61,17 @@ static int ctx_setup(nlk_ctx* c) {
   }
   if (dev_upload(c, &dm.gs_off, hm.gs_off) || dev_upload(c, &dm.gs_idx, hm.gs_idx)) return 1;
   dm.ngs = (int)hm.gs_off.size() - 1;
+  {
+    std::vector<int32_t> g2, g4, ro(1, 0), ri;
+    for (int g = 0; g < dm.ngs; ++g) {
+      const int b_ = hm.gs_off[g], n_ = hm.gs_off[g + 1] - b_;
+      if (n_ == 2) { g2.push_back(hm.gs_idx[b_]); g2.push_back(hm.gs_idx[b_ + 1]); }
+      else if (n_ == 4) { for (int t = 0; t < 4; ++t) g4.push_back(hm.gs_idx[b_ + t]); }
+      else { for (int t = 0; t < n_; ++t) ri.push_back(hm.gs_idx[b_ + t]); ro.push_back((int32_t)ri.size()); }
+    }
+    dm.ngs2 = (int)g2.size() / 2; dm.ngs4 = (int)g4.size() / 4; dm.ngsr = (int)ro.size() - 1;
+    if (dev_upload(c, &dm.gs2, g2) || dev_upload(c, &dm.gs4, g4) || dev_upload(c, &dm.gsr_off, ro) || dev_upload(c, &dm.gsr_idx, ri)) return 1;
+  }
   if (dev_upload(c, &dm.vertex, hm.vertex_local) || dev_upload(c, &dm.vert_off, hm.vert_off) || dev_upload(c, &dm.vert_ec, hm.vert_ec)) return 1;
   for (int k = 0; k < d; ++k) if (dev_upload(c, &c->xyz[k], hm.xyz[k])) return 1;
   if (dev_upload(c, &c->d_lglel, hm.lglel)) return 1;
@@ -83,6 +94,7 @@ static int ctx_setup(nlk_ctx* c) {
   if (dev_alloc(c, &c->d_sc, 1) || dev_alloc(c, &c->d_red, 512)) return 1;
   NLK_CUDA(cudaMallocHost((void**)&c->h_sc, sizeof(SolverScal)));
   NLK_CUDA(cudaMallocHost((void**)&c->h_red, sizeof(double) * 512));
+  NLK_CUDA(cudaMallocHost((void**)&c->h_seq, sizeof(unsigned int) * 16)); c->h_seq[0] = 0; c->seq = 0;
   c->red.maxblocks = 2048;
   if (dev_alloc(c, &c->red.partial, (size_t)16 * c->red.maxblocks) || dev_alloc(c, &c->red.counter, 1)) return 1;
   // state + work arrays
@@ -265,7 +277,7 @@ int nlk_ctx_create(const nlk_mesh* m, const nlk_params* p, int32_t device, nlk_c
   nlk_ctx* c = new nlk_ctx(); c->mesh = m; c->prm = *p; c->device = device;
   NLK_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
   c->ph.on = getenv("NLK_PHASES") != nullptr;
-  if (m->hm.nranks <= 1 && !getenv("NLK_NO_STREAM2")) {
+  if (!getenv("NLK_NO_STREAM2")) {
     // highest priority: the coarse branch is a chain of tiny kernels whose blocks must slip in between the waves of the
     // Schwarz kernels on the main stream instead of queueing behind each of them
     int prio_lo = 0, prio_hi = 0;
@@ -287,6 +299,9 @@ int nlk_ctx_comm_init(nlk_ctx* c, const char id[128], int32_t rank, int32_t nran
     int r = c->nccl.CommInitRank(&c->nccl.comm, nranks, u, rank);
     if (r) { set_error(std::string("ncclCommInitRank failed: ") + c->nccl.GetErrorString(r)); return 1; }
     c->nccl.rank = rank; c->nccl.nranks = nranks;
+    if (c->nccl.CommSplit && c->st2 && !getenv("NLK_NO_COMM2")) {
+      if (c->nccl.CommSplit(c->nccl.comm, 0, rank, &c->nccl.comm2, nullptr) != 0) c->nccl.comm2 = nullptr;     // fall back to the single-stream path
+    }
   }
   return ctx_setup(c);
 }
@@ -307,6 +322,8 @@ int nlk_ctx_destroy(nlk_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   if (c->h_sc) cudaFreeHost(c->h_sc);
   if (c->h_red) cudaFreeHost(c->h_red);
+  if (c->h_seq) cudaFreeHost(c->h_seq);
+  if (c->nccl.comm2) c->nccl.CommDestroy(c->nccl.comm2);
   if (c->nccl.comm) c->nccl.CommDestroy(c->nccl.comm);
   if (c->st2) { cudaStreamSynchronize(c->st2); cudaStreamDestroy(c->st2); cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_crs); }
   cudaStreamDestroy(c->st);

@@ -13,10 +13,12 @@ struct NcclId { char internal[128]; };
 struct Nccl {
   void* lib = nullptr;
   void* comm = nullptr;
+  void* comm2 = nullptr;                 // ncclCommSplit copy used by the side stream (coarse branch of the preconditioner)
   int rank = 0, nranks = 1;
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, NcclId /*ncclUniqueId by value*/, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
+  int (*CommSplit)(void*, int, int, void**, void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
@@ -79,7 +81,8 @@ struct nlk_ctx {
   nlk::SolverScal* d_sc = nullptr;       // device
   nlk::SolverScal* h_sc = nullptr;       // pinned mirror
   double* d_red = nullptr;               // device scratch scalars [64 + lgmres]
-  double* h_red = nullptr;               // pinned mirror
+  double* h_red = nullptr;               // pinned mirror (UVA: device kernels can write it directly)
+  unsigned int* h_seq = nullptr; unsigned int seq = 0;   // publish sequence number of the zero-copy scalar read-back
   nlk::Reducer red{};
   // coordinates (rand field) and misc
   double* xyz[3] = {nullptr, nullptr, nullptr};

@@ -50,6 +50,10 @@ struct DevMesh {
   // gather-scatter
   int32_t *gs_off, *gs_idx;
   int ngs;
+  // the same groups split by multiplicity for launch_gs: dense index pairs / quadruples (no offset array, one vector load per
+  // group) and a CSR for the rest; each list keeps the owner-address order of the full CSR
+  int32_t *gs2 = nullptr, *gs4 = nullptr, *gsr_off = nullptr, *gsr_idx = nullptr;
+  int ngs2 = 0, ngs4 = 0, ngsr = 0;
   // Schwarz / coarse
   double* fdmS;     // [E][d][n*n]
   double* fdmSt;    // transposes
@@ -163,6 +167,8 @@ bool tp_swf_b(const DevMesh& dm, const double* zint, const double* ZF, const int
 void launch_coarse_part_w(const DevMesh& dm, const double* r, const double* mul, double* part, cudaStream_t st);
 void launch_swf_pack(const double* src, const double* mul, const int32_t* idx, int n, double* out, cudaStream_t st);
 void launch_vert_gather(const DevMesh& dm, const double* part, double* rc, cudaStream_t st);
+// zero-copy scalar read-back: one thread copies `count` doubles into pinned host memory, fences, then publishes `seq`
+void launch_publish(const double* d_src, int count, double* h_dst, unsigned int* h_seq, unsigned int seq, cudaStream_t st);
 // exptA_proj_linop `proj_alpha`: per plane group, a_c = <2 u cv>, a_s = <2 u sv> (bm1-weighted); then u = cv a_c + sv a_s
 void launch_planar_proj(double* u, const double* bm1, const double* cv, const double* sv, const int32_t* off, const int32_t* idx, const int32_t* gid,
                         int64_t ngroups, size_t N1, double* coef, cudaStream_t st);

@@ -400,33 +400,36 @@ void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, 
 }
 
 // ------------------------------------------------------------------------------------------------ K2 dssum
-// One thread per shared global node.  Groups of 2 (face-interior nodes: three quarters of all groups) and 4 (edge-interior nodes
-// of a conforming hex mesh) are handled with all index loads, then all value loads, issued together -- the generic loop chains
-// two dependent loads per copy.  Copies are always summed in ascending local order (deterministic, identical on every copy).
+// Direct-stiffness sum over the shared nodes, one thread per group.  The groups are split by multiplicity at set-up:
+//   pairs (face-interior nodes, three quarters of all groups)  -> one int2 load gives both local indices,
+//   quadruples (edge-interior nodes of a conforming hex mesh)  -> one int4 load,
+//   the rest (vertices, irregular edges)                        -> CSR.
+// All index loads, then all value loads of a group are issued together (the r01 kernel chained offset -> index -> value loads
+// per copy).  Copies are always summed in ascending local order: deterministic and identical on every copy.
 template <int NF>
-__global__ void k_gs(Ptr3 f, const int32_t* __restrict__ off, const int32_t* __restrict__ idx, int ngs) {
+__global__ void __launch_bounds__(128)
+k_gs(Ptr3 f, const int2* __restrict__ g2, int n2, const int4* __restrict__ g4, int n4, const int32_t* __restrict__ off, const int32_t* __restrict__ idx, int nr) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= ngs) return;
-  const int b = off[g], n = off[g + 1] - b;
   double* const u0 = f.p[0]; double* const u1 = NF > 1 ? f.p[1] : nullptr; double* const u2 = NF > 2 ? f.p[2] : nullptr;
-  if (n == 2) {
-    const int i0 = idx[b], i1 = idx[b + 1];
-    double a0 = u0[i0], a1 = u0[i1], b0 = 0, b1 = 0, c0 = 0, c1 = 0;
-    if (NF > 1) { b0 = u1[i0]; b1 = u1[i1]; }
-    if (NF > 2) { c0 = u2[i0]; c1 = u2[i1]; }
-    const double sa = a0 + a1; u0[i0] = sa; u0[i1] = sa;
-    if (NF > 1) { const double sb = b0 + b1; u1[i0] = sb; u1[i1] = sb; }
-    if (NF > 2) { const double sc_ = c0 + c1; u2[i0] = sc_; u2[i1] = sc_; }
-  } else if (n == 4) {
-    const int i0 = idx[b], i1 = idx[b + 1], i2 = idx[b + 2], i3 = idx[b + 3];
-    double a[4] = {u0[i0], u0[i1], u0[i2], u0[i3]}, bb[4] = {0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};
-    if (NF > 1) { bb[0] = u1[i0]; bb[1] = u1[i1]; bb[2] = u1[i2]; bb[3] = u1[i3]; }
-    if (NF > 2) { cc[0] = u2[i0]; cc[1] = u2[i1]; cc[2] = u2[i2]; cc[3] = u2[i3]; }
-    const double sa = ((a[0] + a[1]) + a[2]) + a[3]; u0[i0] = sa; u0[i1] = sa; u0[i2] = sa; u0[i3] = sa;
-    if (NF > 1) { const double sb = ((bb[0] + bb[1]) + bb[2]) + bb[3]; u1[i0] = sb; u1[i1] = sb; u1[i2] = sb; u1[i3] = sb; }
-    if (NF > 2) { const double sc_ = ((cc[0] + cc[1]) + cc[2]) + cc[3]; u2[i0] = sc_; u2[i1] = sc_; u2[i2] = sc_; u2[i3] = sc_; }
-  } else {
-    const int e = b + n;
+  if (g < n2) {
+    const int2 ii = g2[g];
+    double a0 = u0[ii.x], a1 = u0[ii.y], b0 = 0, b1 = 0, c0 = 0, c1 = 0;
+    if (NF > 1) { b0 = u1[ii.x]; b1 = u1[ii.y]; }
+    if (NF > 2) { c0 = u2[ii.x]; c1 = u2[ii.y]; }
+    const double sa = a0 + a1; u0[ii.x] = sa; u0[ii.y] = sa;
+    if (NF > 1) { const double sb = b0 + b1; u1[ii.x] = sb; u1[ii.y] = sb; }
+    if (NF > 2) { const double sc_ = c0 + c1; u2[ii.x] = sc_; u2[ii.y] = sc_; }
+  } else if (g < n2 + n4) {
+    const int4 ii = g4[g - n2];
+    double a[4] = {u0[ii.x], u0[ii.y], u0[ii.z], u0[ii.w]}, bb[4] = {0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};
+    if (NF > 1) { bb[0] = u1[ii.x]; bb[1] = u1[ii.y]; bb[2] = u1[ii.z]; bb[3] = u1[ii.w]; }
+    if (NF > 2) { cc[0] = u2[ii.x]; cc[1] = u2[ii.y]; cc[2] = u2[ii.z]; cc[3] = u2[ii.w]; }
+    const double sa = ((a[0] + a[1]) + a[2]) + a[3]; u0[ii.x] = sa; u0[ii.y] = sa; u0[ii.z] = sa; u0[ii.w] = sa;
+    if (NF > 1) { const double sb = ((bb[0] + bb[1]) + bb[2]) + bb[3]; u1[ii.x] = sb; u1[ii.y] = sb; u1[ii.z] = sb; u1[ii.w] = sb; }
+    if (NF > 2) { const double sc_ = ((cc[0] + cc[1]) + cc[2]) + cc[3]; u2[ii.x] = sc_; u2[ii.y] = sc_; u2[ii.z] = sc_; u2[ii.w] = sc_; }
+  } else if (g < n2 + n4 + nr) {
+    const int gg = g - n2 - n4;
+    const int b = off[gg], e = off[gg + 1];
 #pragma unroll
     for (int c = 0; c < NF; ++c) {
       double* u = c == 0 ? u0 : (c == 1 ? u1 : u2);
@@ -438,9 +441,11 @@ __global__ void k_gs(Ptr3 f, const int32_t* __restrict__ off, const int32_t* __r
 }
 void launch_gs(const DevMesh& dm, Ptr3 f, int nf, cudaStream_t st) {
   if (dm.ngs == 0) return;
-  if (nf == 1) k_gs<1><<<cdiv(dm.ngs, 128), 128, 0, st>>>(f, dm.gs_off, dm.gs_idx, dm.ngs);
-  else if (nf == 2) k_gs<2><<<cdiv(dm.ngs, 128), 128, 0, st>>>(f, dm.gs_off, dm.gs_idx, dm.ngs);
-  else k_gs<3><<<cdiv(dm.ngs, 128), 128, 0, st>>>(f, dm.gs_off, dm.gs_idx, dm.ngs);
+  const int nt = dm.ngs2 + dm.ngs4 + dm.ngsr;
+  const int2* g2 = reinterpret_cast<const int2*>(dm.gs2); const int4* g4 = reinterpret_cast<const int4*>(dm.gs4);
+  if (nf == 1) k_gs<1><<<cdiv(nt, 128), 128, 0, st>>>(f, g2, dm.ngs2, g4, dm.ngs4, dm.gsr_off, dm.gsr_idx, dm.ngsr);
+  else if (nf == 2) k_gs<2><<<cdiv(nt, 128), 128, 0, st>>>(f, g2, dm.ngs2, g4, dm.ngs4, dm.gsr_off, dm.gsr_idx, dm.ngsr);
+  else k_gs<3><<<cdiv(nt, 128), 128, 0, st>>>(f, g2, dm.ngs2, g4, dm.ngs4, dm.gsr_off, dm.gsr_idx, dm.ngsr);
   LAUNCH_COUNT();
 }
 
@@ -1109,6 +1114,15 @@ void launch_planar_proj(double* u, const double* bm1, const double* cv, const do
                         int64_t ngroups, size_t N1, double* coef, cudaStream_t st) {
   k_planar_avg<<<cdiv((size_t)ngroups, 4), 128, 0, st>>>(u, bm1, cv, sv, off, idx, ngroups, coef); LAUNCH_COUNT();
   k_planar_apply<<<std::min(cdiv(N1, 256), 148 * 8), 256, 0, st>>>(u, cv, sv, gid, coef, N1); LAUNCH_COUNT();
+}
+__global__ void k_publish(const double* __restrict__ src, int count, double* __restrict__ h_dst, volatile unsigned int* h_seq, unsigned int seq) {
+  for (int i = threadIdx.x; i < count; i += blockDim.x) h_dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) { *h_seq = seq; __threadfence_system(); }
+}
+void launch_publish(const double* d_src, int count, double* h_dst, unsigned int* h_seq, unsigned int seq, cudaStream_t st) {
+  k_publish<<<1, 64, 0, st>>>(d_src, count, h_dst, h_seq, seq); LAUNCH_COUNT();
 }
 void launch_vert_gather(const DevMesh& dm, const double* part, double* rc, cudaStream_t st) {
   k_vert_gather<<<cdiv(dm.nvert, 128), 128, 0, st>>>(part, dm.vert_off, dm.vert_ec, rc, dm.nvert); LAUNCH_COUNT();

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace nlk {
 
@@ -23,6 +24,7 @@ int nccl_load(Nccl& n) {
   NLK_SYM(AllReduce, "ncclAllReduce") NLK_SYM(Send, "ncclSend") NLK_SYM(Recv, "ncclRecv") NLK_SYM(GroupStart, "ncclGroupStart")
   NLK_SYM(GroupEnd, "ncclGroupEnd") NLK_SYM(GetErrorString, "ncclGetErrorString")
 #undef NLK_SYM
+  *(void**)(&n.CommSplit) = dlsym(n.lib, "ncclCommSplit");       // optional (NCCL >= 2.18)
   return 0;
 }
 #define NLK_NCCL(c, call) do { int _r = (call); if (_r != 0) { set_error(std::string("NCCL error: ") + (c)->nccl.GetErrorString(_r)); return 1; } } while (0)
@@ -30,7 +32,8 @@ static const int NCCL_DOUBLE = 8, NCCL_SUM = 0, NCCL_MAX = 2;
 
 int ctx_allreduce(nlk_ctx* c, double* d_ptr, int count, bool maxop) {
   if (c->nccl.nranks <= 1) return 0;
-  NLK_NCCL(c, c->nccl.AllReduce(d_ptr, d_ptr, (size_t)count, NCCL_DOUBLE, maxop ? NCCL_MAX : NCCL_SUM, c->nccl.comm, c->st));
+  void* comm = (c->st == c->st2 && c->nccl.comm2) ? c->nccl.comm2 : c->nccl.comm;      // side stream -> its own communicator
+  NLK_NCCL(c, c->nccl.AllReduce(d_ptr, d_ptr, (size_t)count, NCCL_DOUBLE, maxop ? NCCL_MAX : NCCL_SUM, comm, c->st));
   return 0;
 }
 
@@ -49,7 +52,28 @@ int ctx_gs(nlk_ctx* c, Ptr3 f, int nf) {
   return 0;
 }
 
+// Host read-back of a few device scalars (FGMRES Hessenberg column, dots, CFL).  Default: a one-block kernel writes them straight
+// into pinned host memory (UVA zero-copy), fences, and publishes a sequence number the host spins on -- no cudaMemcpyAsync +
+// cudaStreamSynchronize round trip on the critical path of every FGMRES iteration (r01 verdict: ~0.13 of 0.85 ms per iteration on
+// the launch-bound configs).  A stream synchronize remains the fallback (NLK_SYNC_READBACK=1, or if the spin times out).
 int ctx_read_scalars(nlk_ctx* c, int count) {
+  static const bool sync_mode = getenv("NLK_SYNC_READBACK") != nullptr;
+  if (!sync_mode && c->h_seq) {
+    const unsigned int seq = ++c->seq;
+    launch_publish(c->d_red, count, c->h_red, c->h_seq, seq, c->st);
+    volatile unsigned int* flag = c->h_seq;
+    for (long spin = 0; *flag != seq; ++spin) {
+      if ((spin & 0xfffff) == 0xfffff) {                     // every ~1M polls: has the stream died, or is it just a long kernel?
+        cudaError_t q = cudaStreamQuery(c->st);
+        if (q != cudaErrorNotReady) {                        // finished (flag will be visible after the sync) or failed
+          NLK_CUDA(cudaStreamSynchronize(c->st)); NLK_CUDA(cudaGetLastError());
+          if (*flag != seq) { set_error("scalar read-back: stream finished without publishing"); return 1; }
+          break;
+        }
+      }
+    }
+    return 0;
+  }
   NLK_CUDA(cudaMemcpyAsync(c->h_red, c->d_red, sizeof(double) * count, cudaMemcpyDeviceToHost, c->st));
   NLK_CUDA(cudaStreamSynchronize(c->st));
   NLK_CUDA(cudaGetLastError());               // launch-configuration errors are not sticky: surface them here
@@ -167,7 +191,9 @@ int apply_precond(nlk_ctx* c, const double* r, double* z, const double* in_mul) 
     return 0;
   }
   // single rank: the coarse branch (restrict -> A0^-1 -> ...) runs on a side stream concurrently with the Schwarz branch
-  const bool side = c->have_coarse && c->st2 && c->nccl.nranks <= 1;
+  // multi-rank: the same, with the allreduce of the coarse right-hand side on a split communicator so that it cannot interleave
+  // with the Schwarz ghost exchange of the main stream
+  const bool side = c->have_coarse && c->st2 && (c->nccl.nranks <= 1 || (c->nccl.comm2 && c->swf));
   if (c->swf && c->prm.precond != 3) {                      // fused Schwarz (pull tables): 2 kernels, prolongation folded into the second
     auto coarse_chain = [&]() -> int {
       launch_coarse_part_w(dm, r, in_mul, c->crs_part, c->st);
