@@ -453,6 +453,10 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
     for (int q = 0; q < PRE; ++q) { const int i = threadIdx.x + q * NT; if (i < np1) W1[(i % n) + PN * (i / n)] = pre[q]; }
   };
   if constexpr (DIM == 3) fetch(sel3(C, 0) + e * np1);
+  // pull THIS element's dealiasing metrics (d*d*m^3 doubles: 124 KB at m = 12, the bulk of the kernel's traffic) into L2 now;
+  // they are consumed after the three interpolations of C, a few microseconds from here (the r01 look-ahead prefetch of FUTURE
+  // elements was removed because it did not survive in L2; this one is used by the same block almost immediately)
+  if constexpr (DIM == 3) prefetch_l2(rxd + e * (size_t)(d * d) * npd, d * d * npd, threadIdx.x, blockDim.x);
   load_mat_t(sI, I1dg, m * n); load_mat_t(sIt, I1dtg, m * n); load_mat_t(sDd, Ddg, m * m);
   __syncthreads();
 #pragma unroll 1
