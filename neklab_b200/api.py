@@ -384,6 +384,48 @@ class nek_dvector:
             pass
 
 
+class nek_ext_dvector:
+    """`nek_ext_dvector` (src/vectors/neklab_vectors.f90:121-147; real_extended_vectors.f90): a `nek_dvector` plus the scalar
+    period `T` of a periodic orbit (and its restart copies `Trst`).  The fields live on the device; `T` is a host scalar exactly as
+    in the reference, where it is one double next to the field arrays.  dot adds T*T' (:243), axpby combines T and -- unlike the
+    fields -- Trst consistently (:193, :210), get_size counts it."""
+
+    def __init__(self, ctx: Context, T: float = 0.0):
+        self.ctx = ctx; self.vec = nek_dvector(ctx); self.T = float(T); self.Trst = [0.0, 0.0]
+
+    def zero(self):
+        self.vec.zero(); self.T = 0.0; self.Trst = [0.0, 0.0]
+
+    def rand(self, ifnorm=False, seed=12345):
+        self.vec.rand(False, seed)
+        self.T = float(np.random.default_rng(seed).random())                     # random_number(self%T) (:117)
+        if ifnorm:
+            self.scal(1.0 / self.norm())
+
+    def scal(self, alpha):
+        self.vec.scal(alpha); self.T *= alpha; self.Trst = [alpha * t for t in self.Trst]
+
+    def axpby(self, alpha, vec: "nek_ext_dvector", beta):
+        self.vec.axpby(alpha, vec.vec, beta)
+        self.T = beta * self.T + alpha * vec.T
+        self.Trst = [beta * a + alpha * b for a, b in zip(self.Trst, vec.Trst)]
+
+    def dot(self, vec: "nek_ext_dvector"):
+        return self.vec.dot(vec.vec) + self.T * vec.T
+
+    def norm(self):
+        return float(np.sqrt(self.dot(self)))
+
+    def get_size(self):
+        return self.vec.get_size() + 1
+
+    def save_rst(self, state: "nek_ext_dvector", irst):
+        self.vec.save_rst(state.vec, irst); self.Trst[irst - 1] = state.T
+
+    def get_rst(self, irst):
+        o = nek_ext_dvector(self.ctx); o.vec = self.vec.get_rst(irst); o.T = self.Trst[irst - 1]; return o
+
+
 class nek_zvector:
     """`nek_zvector` (src/vectors/neklab_vectors.f90:219-237): complex vector as a (re, im) pair of `nek_dvector`."""
 

@@ -406,46 +406,33 @@ void launch_axhelm_cg(const DevMesh& dm, double* p, const double* r, double* w, 
 //   the rest (vertices, irregular edges)                        -> CSR.
 // All index loads, then all value loads of a group are issued together (the r01 kernel chained offset -> index -> value loads
 // per copy).  Copies are always summed in ascending local order: deterministic and identical on every copy.
-template <int NF>
 __global__ void __launch_bounds__(128)
 k_gs(Ptr3 f, const int2* __restrict__ g2, int n2, const int4* __restrict__ g4, int n4, const int32_t* __restrict__ off, const int32_t* __restrict__ idx, int nr) {
+  // one grid row (blockIdx.y) per field: the rows are scheduled one after the other, so each field's surface lines stay in L2
+  // between their read and their write (three fields per thread measured 186 us against 3 x 51 us, ncu: 927 vs 660 MB of DRAM)
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  double* const u0 = f.p[0]; double* const u1 = NF > 1 ? f.p[1] : nullptr; double* const u2 = NF > 2 ? f.p[2] : nullptr;
+  double* const u = blockIdx.y == 0 ? f.p[0] : (blockIdx.y == 1 ? f.p[1] : f.p[2]);
   if (g < n2) {
     const int2 ii = g2[g];
-    double a0 = u0[ii.x], a1 = u0[ii.y], b0 = 0, b1 = 0, c0 = 0, c1 = 0;
-    if (NF > 1) { b0 = u1[ii.x]; b1 = u1[ii.y]; }
-    if (NF > 2) { c0 = u2[ii.x]; c1 = u2[ii.y]; }
-    const double sa = a0 + a1; u0[ii.x] = sa; u0[ii.y] = sa;
-    if (NF > 1) { const double sb = b0 + b1; u1[ii.x] = sb; u1[ii.y] = sb; }
-    if (NF > 2) { const double sc_ = c0 + c1; u2[ii.x] = sc_; u2[ii.y] = sc_; }
+    const double a0 = u[ii.x], a1 = u[ii.y];
+    const double sa = a0 + a1; u[ii.x] = sa; u[ii.y] = sa;
   } else if (g < n2 + n4) {
     const int4 ii = g4[g - n2];
-    double a[4] = {u0[ii.x], u0[ii.y], u0[ii.z], u0[ii.w]}, bb[4] = {0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};
-    if (NF > 1) { bb[0] = u1[ii.x]; bb[1] = u1[ii.y]; bb[2] = u1[ii.z]; bb[3] = u1[ii.w]; }
-    if (NF > 2) { cc[0] = u2[ii.x]; cc[1] = u2[ii.y]; cc[2] = u2[ii.z]; cc[3] = u2[ii.w]; }
-    const double sa = ((a[0] + a[1]) + a[2]) + a[3]; u0[ii.x] = sa; u0[ii.y] = sa; u0[ii.z] = sa; u0[ii.w] = sa;
-    if (NF > 1) { const double sb = ((bb[0] + bb[1]) + bb[2]) + bb[3]; u1[ii.x] = sb; u1[ii.y] = sb; u1[ii.z] = sb; u1[ii.w] = sb; }
-    if (NF > 2) { const double sc_ = ((cc[0] + cc[1]) + cc[2]) + cc[3]; u2[ii.x] = sc_; u2[ii.y] = sc_; u2[ii.z] = sc_; u2[ii.w] = sc_; }
+    const double a0 = u[ii.x], a1 = u[ii.y], a2 = u[ii.z], a3 = u[ii.w];
+    const double sa = ((a0 + a1) + a2) + a3; u[ii.x] = sa; u[ii.y] = sa; u[ii.z] = sa; u[ii.w] = sa;
   } else if (g < n2 + n4 + nr) {
     const int gg = g - n2 - n4;
     const int b = off[gg], e = off[gg + 1];
-#pragma unroll
-    for (int c = 0; c < NF; ++c) {
-      double* u = c == 0 ? u0 : (c == 1 ? u1 : u2);
-      double s = 0;
-      for (int t = b; t < e; ++t) s += u[idx[t]];
-      for (int t = b; t < e; ++t) u[idx[t]] = s;
-    }
+    double s = 0;
+    for (int t = b; t < e; ++t) s += u[idx[t]];
+    for (int t = b; t < e; ++t) u[idx[t]] = s;
   }
 }
 void launch_gs(const DevMesh& dm, Ptr3 f, int nf, cudaStream_t st) {
   if (dm.ngs == 0) return;
   const int nt = dm.ngs2 + dm.ngs4 + dm.ngsr;
   const int2* g2 = reinterpret_cast<const int2*>(dm.gs2); const int4* g4 = reinterpret_cast<const int4*>(dm.gs4);
-  if (nf == 1) k_gs<1><<<cdiv(nt, 128), 128, 0, st>>>(f, g2, dm.ngs2, g4, dm.ngs4, dm.gsr_off, dm.gsr_idx, dm.ngsr);
-  else if (nf == 2) k_gs<2><<<cdiv(nt, 128), 128, 0, st>>>(f, g2, dm.ngs2, g4, dm.ngs4, dm.gsr_off, dm.gsr_idx, dm.ngsr);
-  else k_gs<3><<<cdiv(nt, 128), 128, 0, st>>>(f, g2, dm.ngs2, g4, dm.ngs4, dm.gsr_off, dm.gsr_idx, dm.ngsr);
+  k_gs<<<dim3(cdiv(nt, 128), nf), 128, 0, st>>>(f, g2, dm.ngs2, g4, dm.ngs4, dm.gsr_off, dm.gsr_idx, dm.ngsr);
   LAUNCH_COUNT();
 }
 

@@ -90,3 +90,22 @@ def test_forcing_registry_slots(nlk_lib):
         with pytest.raises(api.NlkError):
             ctx.set_forcing(force, ipert=bad)
     ctx.close()
+
+
+def test_ext_dvector_semantics(small):
+    """nek_ext_dvector (src/vectors/real_extended_vectors.f90): fields on the device + the period T as one more degree of freedom."""
+    from neklab_b200 import api
+    om, ctx = small
+    a = api.nek_ext_dvector(ctx); b = api.nek_ext_dvector(ctx)
+    a.rand(False, 3); b.rand(False, 4)
+    assert 0.0 <= a.T < 1.0 and a.T != b.T
+    d0 = a.vec.dot(b.vec)
+    assert abs(a.dot(b) - (d0 + a.T * b.T)) < 1e-14 * abs(d0)                  # :243
+    assert a.get_size() == a.vec.get_size() + 1
+    Ta, Tb = a.T, b.T
+    a.axpby(2.0, b, 3.0)                                                       # :193
+    assert abs(a.T - (3.0 * Ta + 2.0 * Tb)) < 1e-15
+    a.scal(0.5); assert abs(a.T - 0.5 * (3.0 * Ta + 2.0 * Tb)) < 1e-15
+    a.save_rst(b, 1); assert a.get_rst(1).T == b.T
+    a.rand(True, 9); assert abs(a.norm() - 1.0) < 1e-13
+    a.zero(); assert a.T == 0.0 and a.norm() == 0.0
