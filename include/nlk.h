@@ -217,6 +217,29 @@ int nlk_svds(nlk_op* op, int32_t nsv, int32_t kdim, double tol, const nlk_vec* x
 int nlk_gmres(nlk_op* op, int32_t minus_identity, const nlk_vec* b, nlk_vec* x, int32_t kdim, double atol, double rtol,
               int32_t maxiter, int32_t transpose, int32_t* info);
 
+/* resolvent_linop%matvec / %rmatvec  (/root/reference/src/linops/resolvent.f90:17-75) on a nek_zvector (re, im):
+ *   tau = 2 pi / |omega| (1 if omega == 0);  b = forced response from rest over tau (evaluate_rhs, :80-112);
+ *   re  = (I - exptA(tau))^-1 b by GMRES(kdim 64, atol 1e-12, rtol 1e-6, transpose = adjoint) (:114-134);
+ *   im  = forced integration over tau/4 from re (evaluate_imaginary_part, :136-166).
+ * The harmonic forcing Re(exp(+-i omega t) f) goes through the perturbation slot of the forcing registry and the
+ * registry is zeroed afterwards, as in the reference.  op supplies the base flow; its tau is restored on return.
+ * rtol <= 0 selects the reference's 1e-6.  info: 0 = GMRES converged. */
+int nlk_resolvent_matvec(nlk_op* op, double omega, const nlk_vec* f_re, const nlk_vec* f_im, nlk_vec* out_re, nlk_vec* out_im,
+                         int32_t adjoint, double rtol, int32_t* info);
+/* one forced integration of the above (evaluate_rhs when x0 == NULL, evaluate_imaginary_part otherwise) */
+int nlk_resolvent_integrate(nlk_op* op, double tau, double omega, const nlk_vec* f_re, const nlk_vec* f_im, int32_t adjoint,
+                            const nlk_vec* x0, nlk_vec* out);
+
+/* nek_upo_jacobian%matvec / %rmatvec  (/root/reference/src/systems/periodic_orbit.f90:46-113 / :115-181) on
+ * nek_ext_dvector = (nek_dvector fields, period T) (/root/reference/src/vectors/real_extended_vectors.f90):
+ *   base flow := X, dt from its CFL at 0.4 with endtime T_X, tolerances atol*0.1 (direct) / atol*0.5 (adjoint), atol = vtol;
+ *   base flow and perturbation advanced TOGETHER (setup_linear_solver(solve_baseflow = .true.)) with the rst protocol of exptA;
+ *   out = u'(T_X) - in + T_in * f'(X(T)),  T_out = <in, f'(X(0))>,  f' = (F_dt(X) - X)/dt (compute_fdot,
+ *   /root/reference/src/systems/neklab_systems.f90:202-223).  On return vtol = ptol = atol as in the reference (:106-107).
+ * The nonlinear map of nek_upo_system (:4-44) is nlk_nonlinear_map with tau = T (the period component of its result is 0). */
+int nlk_upo_jacobian(nlk_ctx* c, const nlk_vec* X, double T_X, const nlk_vec* in, double T_in, nlk_vec* out, double* T_out,
+                     int32_t transpose);
+
 /* ------------------------------------------------------------------ kernel-level test/bench hooks
  * (the K-numbered kernels of SURVEY §2.3; host arrays in, host arrays out unless noted) */
 int nlk_test_axhelm(nlk_ctx* c, const double* u, double h1, double h2, double* w);          /* K1, local (no dssum) */

@@ -57,7 +57,7 @@ nlk_ctx_set_dt nlk_comm_unique_id nlk_ctx_comm_init nlk_ctx_sync nlk_ctx_stream 
 nlk_vec_rand nlk_vec_scal nlk_vec_axpby nlk_vec_dot nlk_vec_norm nlk_vec_size nlk_vec_save_rst nlk_vec_get_rst nlk_vec_nrst
 nlk_vec_clear_rst nlk_vec_upload nlk_vec_download nlk_zvec_scal nlk_zvec_axpby nlk_zvec_dot nlk_basis_innerprod nlk_basis_axpy nlk_basis_dgs nlk_exptA_create
 nlk_exptA_destroy nlk_exptA_init nlk_exptA_set_tau nlk_exptA_matvec nlk_exptA_rmatvec nlk_exptA_stats nlk_exptA_time_steps nlk_exptA_set_baseflow nlk_exptA_set_projection nlk_exptA_apply_projection nlk_nonlinear_map nlk_newton_fixed_point nlk_ctx_set_forcing nlk_set_neklab_forcing nlk_get_neklab_forcing nlk_zero_neklab_forcing nlk_zero_neklab_forcing_ipert nlk_nek2vec nlk_vec2nek
-nlk_eigs nlk_svds nlk_gmres nlk_test_axhelm nlk_test_dssum nlk_test_opdiv nlk_test_opgradt nlk_test_cdabdtp nlk_test_convect
+nlk_eigs nlk_svds nlk_gmres nlk_resolvent_matvec nlk_resolvent_integrate nlk_upo_jacobian nlk_test_axhelm nlk_test_dssum nlk_test_opdiv nlk_test_opgradt nlk_test_cdabdtp nlk_test_convect
 nlk_test_convect_adj nlk_test_helmholtz nlk_test_pressure nlk_test_precond nlk_test_cfl nlk_bench_kernel""".split()
 
 
@@ -222,6 +222,7 @@ class Context:
 
     def set_tol(self, vtol, ptol):
         _chk(lib().nlk_ctx_set_tol(self.h, C.c_double(vtol), C.c_double(ptol)))
+        self.params.vtol = vtol; self.params.ptol = ptol
 
     def set_dt(self, dt):
         _chk(lib().nlk_ctx_set_dt(self.h, C.c_double(dt)))
@@ -509,6 +510,38 @@ class exptA_linop:
             pass
 
 
+class resolvent_linop:
+    """`resolvent_linop` (src/linops/neklab_linops.f90:198-205, src/linops/resolvent.f90): R(i omega) on a `nek_zvector`, evaluated
+    by time stepping: forced response over one period, GMRES on I - exptA for the periodic state, a quarter period for the
+    imaginary part."""
+
+    def __init__(self, ctx: Context, omega: float, baseflow: nek_dvector, rtol: float = 0.0):
+        self.ctx = ctx; self.omega = float(omega); self.rtol = rtol
+        self._A = exptA_linop(ctx, 1.0, baseflow)
+        self.info = None
+
+    def _apply(self, vec_in: "nek_zvector", vec_out, adjoint):
+        vec_out = vec_out or nek_zvector(self.ctx)
+        info = C.c_int32()
+        _chk(lib().nlk_resolvent_matvec(self._A.h, C.c_double(self.omega), vec_in.re.h, vec_in.im.h, vec_out.re.h, vec_out.im.h,
+                                        C.c_int32(1 if adjoint else 0), C.c_double(self.rtol), C.byref(info)))
+        self.info = info.value
+        return vec_out
+
+    def matvec(self, vec_in, vec_out=None):
+        return self._apply(vec_in, vec_out, False)
+
+    def rmatvec(self, vec_in, vec_out=None):
+        return self._apply(vec_in, vec_out, True)
+
+    def integrate(self, tau, forcing: "nek_zvector", x0: nek_dvector | None = None, adjoint=False) -> nek_dvector:
+        """`evaluate_rhs` (x0 None, resolvent.f90:80-112) / `evaluate_imaginary_part` (:136-166)."""
+        out = nek_dvector(self.ctx)
+        _chk(lib().nlk_resolvent_integrate(self._A.h, C.c_double(tau), C.c_double(self.omega), forcing.re.h, forcing.im.h,
+                                           C.c_int32(1 if adjoint else 0), x0.h if x0 is not None else None, out.h))
+        return out
+
+
 # ---- mesh-1 <-> mesh-2 pressure maps and field-file I/O (Nek `mappr` / `load_fld` / `outpost`; src/neklab_utils.f90:305-361)
 def _tensor(M, a, ndim):
     a = np.einsum("pi,ezyi->ezyp", M, a)
@@ -559,6 +592,50 @@ def nonlinear_map(ctx: Context, tau, vec_in: nek_dvector, cfl_limit=0.4) -> nek_
     out = nek_dvector(ctx)
     _chk(lib().nlk_nonlinear_map(ctx.h, C.c_double(tau), C.c_double(cfl_limit), vec_in.h, out.h))
     return out
+
+
+class nek_upo_system:
+    """`nek_upo_system%response` (src/systems/periodic_orbit.f90:4-44): F_T(X) - X with T the period carried by the vector,
+    dt from the CFL of X at 0.4, vtol = ptol = atol*0.1; the period component of the residual is T - T = 0."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    def response(self, vec_in: nek_ext_dvector, atol: float) -> nek_ext_dvector:
+        ctx = self.ctx
+        vt, pt = ctx.params.vtol, ctx.params.ptol
+        ctx.set_tol(atol * 0.1, atol * 0.1)
+        try:
+            out = nek_ext_dvector(ctx)
+            _chk(lib().nlk_nonlinear_map(ctx.h, C.c_double(vec_in.T), C.c_double(0.4), vec_in.vec.h, out.vec.h))
+            out.T = vec_in.T - vec_in.T
+        finally:
+            ctx.set_tol(vt, pt)
+        return out
+
+
+class nek_upo_jacobian:
+    """`nek_upo_jacobian` (src/systems/neklab_systems.f90:157-164; periodic_orbit.f90:46-181): Jacobian of the periodic-orbit
+    residual at `X` = (X(0), T) on `nek_ext_dvector`s -- base flow and perturbation advanced together over T, the period column
+    f'(X(T)) dT and the phase-condition row <dx, f'(X(0))>."""
+
+    def __init__(self, ctx: Context, X: nek_ext_dvector):
+        self.ctx = ctx; self.X = X
+
+    def _apply(self, vec_in: nek_ext_dvector, vec_out, transpose):
+        vec_out = vec_out or nek_ext_dvector(self.ctx)
+        T = C.c_double()
+        _chk(lib().nlk_upo_jacobian(self.ctx.h, self.X.vec.h, C.c_double(self.X.T), vec_in.vec.h, C.c_double(vec_in.T), vec_out.vec.h,
+                                    C.byref(T), C.c_int32(1 if transpose else 0)))
+        vec_out.T = T.value
+        p = self.ctx.params; p.ptol = p.vtol                     # the call leaves vtol = ptol = atol, as the reference does
+        return vec_out
+
+    def matvec(self, vec_in, vec_out=None):
+        return self._apply(vec_in, vec_out, False)
+
+    def rmatvec(self, vec_in, vec_out=None):
+        return self._apply(vec_in, vec_out, True)
 
 
 def newton_fixed_point_iteration(ctx: Context, bf: nek_dvector, tol, tau=1.0, tol_mode=1, maxiter=40, gmres_kdim=30):

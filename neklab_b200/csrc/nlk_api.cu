@@ -327,6 +327,7 @@ int nlk_ctx_destroy(nlk_ctx* c) {
   if (c->nccl.comm) c->nccl.CommDestroy(c->nccl.comm);
   if (c->st2) { cudaStreamSynchronize(c->st2); cudaStreamDestroy(c->st2); cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_crs); }
   cudaStreamDestroy(c->st);
+  delete c->bank2;
   delete c; return 0;
 }
 int nlk_ctx_set_tol(nlk_ctx* c, double vtol, double ptol) { c->prm.vtol = vtol; c->prm.ptol = ptol; return 0; }
@@ -742,6 +743,143 @@ int nlk_exptA_time_steps(nlk_op* op, const nlk_vec* in, int32_t nwarm, int32_t n
   op->stats.nsteps = c->nsteps; op->stats.dt = c->dt; op->stats.ms_total = ms; op->stats.launches = g_launches - l0;
   op->stats.cg_iters = c->cg_iters - cg0; op->stats.gmres_iters = c->gmres_iters - gm0; op->stats.steps = c->steps - st0;
   return 0;
+}
+// resolvent_linop (src/linops/resolvent.f90): evaluate_rhs (:80-112) / evaluate_imaginary_part (:136-166) are the same loop --
+// time-harmonic forcing Re(exp(+-i omega t) f) written into the perturbation slot of the forcing registry before every step --
+// started from zero (x0 == nullptr) or from x0.  The forcing is combined on the device (no host copy of the fields per step).
+static int resolvent_integrate(nlk_op* op, double tau, double omega, const nlk_vec* fre, const nlk_vec* fim, bool adjoint, const nlk_vec* x0, nlk_vec* out) {
+  nlk_ctx* c = op->c; const DevMesh& dm = c->dm;
+  if (push_baseflow(op)) return 1;
+  if (step_setup(c, tau, adjoint)) return 1;                      // exptA%init(): setup_linear_solver(endtime = tau) -> nsteps, dt
+  if (x0) { if (state_from_vec(c, x0->v, x0->pr, x0->theta)) return 1; }
+  else {                                                         // opzero(vxp, vyp, vzp); the stale prp/tp of the reference are zeroed too
+    for (int k = 0; k < dm.ndim; ++k) NLK_CUDA(cudaMemsetAsync(c->vp[k], 0, dm.N1 * sizeof(double), c->st));
+    NLK_CUDA(cudaMemsetAsync(c->prp, 0, dm.N2 * sizeof(double), c->st));
+    NLK_CUDA(cudaMemsetAsync(c->tp, 0, dm.N1 * sizeof(double), c->st));
+  }
+  if (reset_history_pub(c)) return 1;
+  for (int k = 0; k < dm.ndim; ++k) if (!c->forcing[1][k]) { if (dev_alloc(c, &c->forcing[1][k], dm.N1)) return 1; }
+  const double sign = adjoint ? -1.0 : 1.0;
+  int rc = 0;
+  for (int istep = 1; istep <= c->nsteps && !rc; ++istep) {
+    const double th = sign * omega * (double)(istep - 1) * c->dt;  // `time` before nek_advance
+    for (int k = 0; k < dm.ndim; ++k)                              // Re((cos + i sin)(f_re + i f_im))
+      launch_lin(c->forcing[1][k], dm.N1, std::cos(th), fre->v[k], -std::sin(th), fim->v[k], 0, nullptr, 0, nullptr, nullptr, c->st);
+    c->has_forcing[1] = true;
+    rc = step_advance(c, istep);
+  }
+  c->has_forcing[0] = c->has_forcing[1] = false;                   // zero_neklab_forcing()
+  c->adjoint = false;
+  if (rc) return 1;
+  if (copy_fields(c, out->v, out->pr, out->theta, c->vp, c->prp, c->tp)) return 1;
+  out->nrst = 0;
+  return sync_cg_counter(c);
+}
+}  // extern "C"
+namespace nlk { int resolvent_apply(nlk_op* op, double omega, const nlk_vec* fre, const nlk_vec* fim, nlk_vec* ore, nlk_vec* oim, bool adjoint, double rtol, int32_t* info); }
+int nlk::resolvent_apply(nlk_op* op, double omega, const nlk_vec* fre, const nlk_vec* fim, nlk_vec* ore, nlk_vec* oim, bool adjoint, double rtol, int32_t* info) {
+  nlk_ctx* c = op->c;
+  if (ore == oim || ore == fre || ore == fim || oim == fre || oim == fim) { set_error("resolvent: input and output vectors must differ"); return 1; }
+  const double tau = omega == 0.0 ? 1.0 : 2.0 * M_PI / std::fabs(omega);
+  const double tau0 = op->tau;
+  nlk_vec* b = nullptr; if (nlk_vec_create(c, &b)) return 1;
+  int rc = 0;
+  do {
+    op->tau = tau;
+    if ((rc = resolvent_integrate(op, tau, omega, fre, fim, adjoint, nullptr, b))) break;           // b = forced response from rest over one period
+    if ((rc = nlk_vec_scal(b, -1.0))) break;                                                        // (I - exptA) x = b  <=>  (exptA - I) x = -b
+    if ((rc = nlk_vec_zero(ore))) break;
+    if ((rc = nlk_gmres(op, 1, b, ore, 64, 1.0e-12, rtol, 10, adjoint ? 1 : 0, info))) break;       // gmres_dp_opts(kdim = 64), atol 1e-12, rtol 1e-6
+    ore->nrst = 0;
+    op->tau = tau / 4.0;
+    rc = resolvent_integrate(op, tau / 4.0, omega, fre, fim, adjoint, ore, oim);                    // quarter period from the periodic state
+  } while (0);
+  op->tau = tau0;
+  nlk_vec_destroy(b);
+  return rc;
+}
+extern "C" {
+// resolvent_matvec / resolvent_rmatvec (src/linops/resolvent.f90:17-75); rtol <= 0 selects the reference's 1e-6
+int nlk_resolvent_matvec(nlk_op* op, double omega, const nlk_vec* fre, const nlk_vec* fim, nlk_vec* ore, nlk_vec* oim, int32_t adjoint, double rtol, int32_t* info) {
+  int32_t dummy = 0;
+  return nlk::resolvent_apply(op, omega, fre, fim, ore, oim, adjoint != 0, rtol > 0 ? rtol : 1.0e-6, info ? info : &dummy);
+}
+// one leg of the above, for tests: the forced integration over tau from x0 (or from rest when x0 is NULL)
+int nlk_resolvent_integrate(nlk_op* op, double tau, double omega, const nlk_vec* fre, const nlk_vec* fim, int32_t adjoint, const nlk_vec* x0, nlk_vec* out) {
+  if (out == fre || out == fim || out == x0) { set_error("resolvent: input and output vectors must differ"); return 1; }
+  return resolvent_integrate(op, tau, omega, fre, fim, adjoint != 0, x0, out);
+}
+// ---- periodic orbits: nek_upo_jacobian (src/systems/periodic_orbit.f90:46-181) on nek_ext_dvector = (fields, T)
+// compute_fdot (src/systems/neklab_systems.f90:202-223): (F_dt(X) - X)/dt with ONE first-order nonlinear step from the base
+// state held in bank2 (the perturbation part of that nek_advance is skipped: nothing reads it afterwards)
+static int upo_fdot(nlk_ctx* c, nlk_vec* vec) {
+  const DevMesh& dm = c->dm;
+  bank_swap(c);
+  int rc = copy_fields(c, vec->v, vec->pr, vec->theta, c->vp, c->prp, c->tp);
+  if (!rc) rc = reset_history_pub(c);
+  c->nonlinear = true; const bool adj = c->adjoint; c->adjoint = false;
+  if (!rc) rc = step_advance(c, 1);
+  c->nonlinear = false; c->adjoint = adj;
+  if (!rc) {
+    const double s = 1.0 / c->dt;
+    for (int k = 0; k < dm.ndim; ++k) launch_lin(vec->v[k], dm.N1, s, c->vp[k], -s, vec->v[k], 0, nullptr, 0, nullptr, nullptr, c->st);
+    launch_lin(vec->pr, dm.N2, s, c->prp, -s, vec->pr, 0, nullptr, 0, nullptr, nullptr, c->st);
+    vec->nrst = 0;
+  }
+  bank_swap(c);
+  return rc;
+}
+int nlk_upo_jacobian(nlk_ctx* c, const nlk_vec* X, double TX, const nlk_vec* in, double Tin, nlk_vec* out, double* Tout, int32_t transpose) {
+  if (in == out || X == out) { set_error("upo jacobian: vec_in / X and vec_out must differ"); return 1; }
+  if (bank2_ensure(c)) return 1;
+  const DevMesh& dm = c->dm; StateBank* b = c->bank2;
+  const int nrst = c->prm.torder - 1;
+  const double atol = c->prm.vtol;                                        // param(22)
+  const double fac = transpose ? 0.5 : 0.1;                               // :68-69 / :137-138
+  nlk_vec* vec = nullptr; if (nlk_vec_create(c, &vec)) return 1;
+  double* Usave[3] = {c->U[0], c->U[1], c->U[2]};
+  int rc = 0;
+  auto base_from_X = [&]() { return copy_fields(c, b->vp, b->prp, b->tp, X->v, X->pr, X->theta); };   // abs_ext_vec2nek(vx, vy, vz, pr, t, self%X)
+  do {
+    c->prm.vtol = atol * fac; c->prm.ptol = atol * fac;
+    if ((rc = base_from_X())) break;
+    if ((rc = step_setup_cfl(c, TX, 0.4, CPtr3{{X->v[0], X->v[1], X->v[2]}}))) break;               // endtime = get_period_abs(self%X), cfl_limit = 0.4
+    c->adjoint = transpose != 0;
+    if ((rc = state_from_vec(c, in->v, in->pr, in->theta))) break;                                    // ext_vec2nek(vxp, ..., vec_in)
+    if ((rc = reset_history_pub(c))) break;
+    bank_swap(c); rc = reset_history_pub(c); bank_swap(c); if (rc) break;
+    for (int k = 0; k < dm.ndim; ++k) c->U[k] = b->vp[k];                                            // the linearisation point is the moving base state
+    for (int istep = 1; istep <= c->nsteps && !rc; ++istep) {
+      rc = coupled_advance(c, istep);
+      if (!rc && istep <= nrst && in->nrst > 0 && c->prm.rst_mode != 2) {                            // jac_get_rst (:216-228)
+        if (istep > in->nrst) { set_error("upo jacobian: input vector has fewer rst fields than the temporal order needs"); rc = 1; break; }
+        rc = state_from_vec(c, in->rv[istep - 1], in->rpr[istep - 1], in->rth[istep - 1]);
+      }
+    }
+    if (rc) break;
+    if ((rc = copy_fields(c, out->v, out->pr, out->theta, c->vp, c->prp, c->tp))) break;              // nek2ext_vec(vec_out, vxp, ...)
+    out->nrst = 0;
+    for (int k = 1; k <= nrst && !rc; ++k) {                                                          // jac_compute_rst (:183-214): the base flow keeps moving too
+      if ((rc = coupled_advance(c, c->nsteps + k))) break;
+      if ((rc = vec_alloc_rst(out, k - 1))) break;
+      rc = copy_fields(c, out->rv[k - 1], out->rpr[k - 1], out->rth[k - 1], c->vp, c->prp, c->tp);
+      out->nrst = std::max(out->nrst, k);
+    }
+    if (rc) break;
+    if ((rc = nlk_vec_axpby(-1.0, in, 1.0, out))) break;                                              // [exp(tau J) - I] dx
+    if ((rc = upo_fdot(c, vec))) break;                                                               // f'(X(T)) from where the base trajectory stands (:93-97)
+    if ((rc = nlk_vec_axpby(Tin, vec, 1.0, out))) break;                                              // + f'(X(T)) dT
+    if ((rc = base_from_X())) break;                                                                  // phase condition at X(0) (:99-103)
+    if ((rc = upo_fdot(c, vec))) break;
+    double d; if ((rc = nlk_vec_dot(in, vec, &d))) break;                                             // vec%T = 0: no period term
+    *Tout = d;
+  } while (0);
+  for (int k = 0; k < 3; ++k) c->U[k] = Usave[k];
+  c->adjoint = false;
+  c->prm.vtol = atol; c->prm.ptol = atol;                                                             // "Reset tolerances": param(22) = param(21) = atol (:106-107)
+  nlk_vec_destroy(vec);
+  if (!rc) rc = sync_cg_counter(c);
+  return rc;
 }
 int nlk_exptA_stats(const nlk_op* op, nlk_stats* out) { *out = op->stats; out->nsteps = op->c->nsteps; out->dt = op->c->dt; return 0; }
 

@@ -65,8 +65,20 @@ struct PhaseScope {
 };
 }  // namespace nlk
 
+namespace nlk {
+// second copy of the time-stepping state: when the base flow is advanced together with the perturbation (Nek `ifbase`,
+// setup_linear_solver(solve_baseflow = .true.), src/neklab_nek_setup.f90:105-106) the nonlinear state and its BDF/EXT history
+// live here and are swapped with the active set around the nonlinear step
+struct StateBank {
+  double* vp[3] = {nullptr, nullptr, nullptr}; double* prp = nullptr; double* tp = nullptr;
+  double* vlag[2][3] = {{nullptr}}; double* exx1[3] = {nullptr}; double* exx2[3] = {nullptr};
+  double* prlag = nullptr; double* proj_X = nullptr; double* proj_EX = nullptr; int nproj = 0;
+};
+}  // namespace nlk
+
 struct nlk_ctx {
   nlk::PhaseTimer ph;
+  nlk::StateBank* bank2 = nullptr;
   const nlk_mesh* mesh = nullptr;
   nlk::DevMesh dm{};
   nlk_params prm{};
@@ -179,6 +191,9 @@ int coarse_setup_sparse(nlk_ctx* c);
 int coarse_solve_sparse(nlk_ctx* c, const double* rc, double* yc);
 int ortho(nlk_ctx* c, double* p);
 int reset_history_pub(nlk_ctx* c);
+int bank2_ensure(nlk_ctx* c);                       // allocate the second state set (lazily, first coupled run)
+void bank_swap(nlk_ctx* c);                          // active state <-> bank2
+int coupled_advance(nlk_ctx* c, int istep);          // one nek_advance with ifbase: perturbation step on U(t^{n-1}), then the nonlinear step of U
 void make_filter_matrix(const Basis& b, double w, double cutoff, std::vector<double>& F);
 void make_fdm_1d(const Basis& b, double lm, double ll, double lr, int bcl, int bcr, double* S, double* lam, int* nact);
 double mesh_diag_local(const HostMesh& hm, int64_t e, int p);

@@ -328,8 +328,13 @@ int nlk_gmres(nlk_op* op, int32_t minus_identity, const nlk_vec* b, nlk_vec* x, 
   const double tol = atol + rtol * bnorm;
   *info = 1;
   for (int outer = 0; outer <= maxiter; ++outer) {
-    if (apply(x, r)) return 1;
-    if (nlk_vec_axpby(1.0, b, -1.0, r)) return 1;               // r = b - A x
+    double xn = 1.0;
+    if (outer == 0) { if (nlk_vec_norm(x, &xn)) return 1; }
+    if (xn == 0.0) { if (nlk_vec_copy(r, b)) return 1; }        // zero initial guess: r = b without a matvec (LightKrylov does the same)
+    else {
+      if (apply(x, r)) return 1;
+      if (nlk_vec_axpby(1.0, b, -1.0, r)) return 1;             // r = b - A x
+    }
     r->nrst = 0;
     double beta; if (nlk_vec_norm(r, &beta)) return 1;
     if (beta < tol) { *info = 0; break; }

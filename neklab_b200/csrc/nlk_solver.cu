@@ -602,6 +602,45 @@ int step_advance(nlk_ctx* c, int istep) {
 }
 
 int reset_history_pub(nlk_ctx* c) { return reset_history(c); }
+
+// ------------------------------------------------------------------------------------------------ coupled base flow + perturbation
+int bank2_ensure(nlk_ctx* c) {
+  if (c->bank2) return 0;
+  if (c->prm.ifheat) { set_error("coupled base-flow/perturbation stepping with temperature is out of scope (nonlinear Boussinesq stepper)"); return 1; }
+  const DevMesh& dm = c->dm;
+  StateBank* b = new StateBank();
+  for (int k = 0; k < dm.ndim; ++k) {
+    if (dev_alloc(c, &b->vp[k], dm.N1) || dev_alloc(c, &b->vlag[0][k], dm.N1) || dev_alloc(c, &b->vlag[1][k], dm.N1) ||
+        dev_alloc(c, &b->exx1[k], dm.N1) || dev_alloc(c, &b->exx2[k], dm.N1)) { delete b; return 1; }
+  }
+  if (dev_alloc(c, &b->prp, dm.N2) || dev_alloc(c, &b->prlag, dm.N2) || dev_alloc(c, &b->tp, dm.N1)) { delete b; return 1; }
+  if (c->prm.pr_proj > 0) {
+    if (dev_alloc(c, &b->proj_X, (size_t)c->prm.pr_proj * dm.N2) || dev_alloc(c, &b->proj_EX, (size_t)c->prm.pr_proj * dm.N2)) { delete b; return 1; }
+  }
+  c->bank2 = b;
+  return 0;
+}
+void bank_swap(nlk_ctx* c) {
+  StateBank* b = c->bank2;
+  for (int k = 0; k < 3; ++k) {
+    std::swap(c->vp[k], b->vp[k]); std::swap(c->vlag[0][k], b->vlag[0][k]); std::swap(c->vlag[1][k], b->vlag[1][k]);
+    std::swap(c->exx1[k], b->exx1[k]); std::swap(c->exx2[k], b->exx2[k]);
+  }
+  std::swap(c->prp, b->prp); std::swap(c->tp, b->tp); std::swap(c->prlag, b->prlag);
+  std::swap(c->proj_X, b->proj_X); std::swap(c->proj_EX, b->proj_EX); std::swap(c->nproj, b->nproj);
+}
+// Nek `nek_advance` with ifpert and ifbase (SURVEY.md call stack: [ifbase -> fluid] fluidp per igeom): the explicit terms of
+// the perturbation (igeom = 1) see the base flow of the previous time level, which is then advanced by the nonlinear step.
+// c->U must alias the base state held in bank2 (the caller sets that up).
+int coupled_advance(nlk_ctx* c, int istep) {
+  if (step_advance(c, istep)) return 1;
+  const bool adj = c->adjoint;
+  bank_swap(c); c->nonlinear = true; c->adjoint = false;
+  const int rc = step_advance(c, istep);
+  c->nonlinear = false; c->adjoint = adj; bank_swap(c);
+  c->steps -= 1;                                      // one nek_advance
+  return rc;
+}
 void make_filter_matrix(const Basis& b, double w, double cutoff, std::vector<double>& F) { filter_matrix(b, w, cutoff, F); }
 void make_fdm_1d(const Basis& b, double lm, double ll, double lr, int bcl, int bcr, double* S, double* lam, int* nact) { fdm_1d(b, lm, ll, lr, bcl, bcr, S, lam, nact); }
 double mesh_diag_local(const HostMesh& hm, int64_t e, int p) { return diag_local(hm, e, p); }

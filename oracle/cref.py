@@ -194,11 +194,25 @@ class CPertStepper:
         L = lib(); U = [_c(u) for u in self.U]; T = _c(self.T)
         L.nekref_set_base(self.ref.h, _p(U[0]), _p(U[1]), _p(U[2]) if self.d == 3 else None, _p(T))
         L.nekref_set_mode(self.ref.h, C.c_double(self.dt), C.c_int(int(self.adjoint)), C.c_int(int(self.nonlinear)))
-        if self.forcing is not None:
-            f = [_c(x) for x in self.forcing]
+        self._push_forcing()
+
+    def _push_forcing(self):
+        L = lib()
+        if self._forcing is not None:
+            f = [_c(x) for x in self._forcing]
             L.nekref_set_forcing(self.ref.h, _p(f[0]), _p(f[1]), _p(f[2]) if self.d == 3 else None)
         else:
             L.nekref_set_forcing(self.ref.h, None, None, None)
+        self._fdirty = False
+
+    # a forcing assigned between two steps (time-dependent forcing: resolvent, OTD) is pushed before the next advance
+    @property
+    def forcing(self):
+        return self._forcing
+
+    @forcing.setter
+    def forcing(self, f):
+        self._forcing = f; self._fdirty = True
 
     def set_state(self, v, p, t=None):
         v = [_c(x) for x in v]; p = _c(p); t = _c(t) if t is not None else np.zeros_like(self.mesh.bm1)
@@ -220,6 +234,8 @@ class CPertStepper:
     def advance(self, istep):
         if getattr(self, "_dirty", True):          # base flow / mode / forcing are pushed once per setup()
             self._push_mode(); self._dirty = False
+        elif self._fdirty:
+            self._push_forcing()
         lib().nekref_advance(self.ref.h, C.c_int(istep))
         cg, gm = self.ref.counters()
         self.stats["cg_iters"] = cg; self.stats["gmres_iters"] = gm

@@ -176,7 +176,10 @@ def gmres(apply, b, x0, kdim=30, atol=ATOL_DP, rtol=RTOL_DP, maxiter=10):
     bnorm = b.norm()
     tol = atol + rtol * bnorm
     for outer in range(maxiter):
-        r = apply(x); r.axpby(1.0, b, -1.0)             # r = b - A x
+        if outer == 0 and x.norm() == 0.0:
+            r = b.copy(); r.nrst = 0                    # zero initial guess: no matvec (LightKrylov skips it too)
+        else:
+            r = apply(x); r.axpby(1.0, b, -1.0)         # r = b - A x
         beta = r.norm()
         if beta < tol:
             break

@@ -693,3 +693,146 @@ class ExptAProj(ExptA):
             out.save_rst(s, k)
         self.nmatvec += 1
         return out
+
+
+# --------------------------------------------------------------------------- resolvent
+class Resolvent:
+    """`resolvent_linop` (src/linops/neklab_linops.f90:198-205; src/linops/resolvent.f90): vec_in = (f_re, f_im) -> (re, im).
+    tau = 2 pi/|omega| (:22); b = evaluate_rhs (:80-112); re = gmres(I - exptA, b) with kdim 64, atol 1e-12, rtol 1e-6
+    (:114-134); im = evaluate_imaginary_part over tau/4 (:136-166)."""
+
+    def __init__(self, stepper: PertStepper, omega: float, baseflow: NekVec, rtol: float = 1.0e-6):
+        self.st, self.omega, self.bf, self.rtol = stepper, float(omega), baseflow, rtol
+
+    def integrate(self, tau, f_re: NekVec, f_im: NekVec, x0: Optional[NekVec] = None, adjoint=False) -> NekVec:
+        st = self.st
+        st.U = [x.copy() for x in self.bf.v]; st.T = self.bf.theta.copy()
+        st.setup(tau, 0.5, adjoint)                                   # exptA%init()
+        z = NekVec(st.mesh, st.prm.torder, st.prm.ifheat)
+        src = x0 if x0 is not None else z                             # opzero(vxp, vyp, vzp)
+        st.set_state(src.v, src.pr, src.theta); st.reset_history()
+        sign = -1.0 if adjoint else 1.0
+        for istep in range(1, st.nsteps + 1):
+            th = sign * self.omega * (istep - 1) * st.dt              # alpha = exp(sign i omega time)
+            st.forcing = [math.cos(th) * f_re.v[c] - math.sin(th) * f_im.v[c] for c in range(st.d)]       # Re(alpha f), ipert = 1
+            st.advance(istep)
+        st.forcing = None                                             # zero_neklab_forcing()
+        st.adjoint = False
+        out = NekVec(st.mesh, st.prm.torder, st.prm.ifheat)
+        out.v = [x.copy() for x in st.vp]; out.pr = st.prp.copy(); out.theta = st.tp.copy()
+        return out
+
+    def _apply(self, f_re, f_im, adjoint):
+        from .krylov import gmres
+        tau = 1.0 if self.omega == 0.0 else 2.0 * math.pi / abs(self.omega)
+        b = self.integrate(tau, f_re, f_im, None, adjoint)
+        A = ExptA(self.st, tau, self.bf)
+
+        def S(x):                                                     # axpby_linop(Id, exptA, 1, -1)
+            y = A._apply(x, adjoint); y.axpby(1.0, x, -1.0)
+            return y
+        x0 = NekVec(self.st.mesh, self.st.prm.torder, self.st.prm.ifheat)
+        re = gmres(S, b, x0, kdim=64, atol=1.0e-12, rtol=self.rtol, maxiter=10)
+        re.nrst = 0
+        im = self.integrate(tau / 4.0, f_re, f_im, re, adjoint)
+        return re, im
+
+    def matvec(self, f_re, f_im):
+        return self._apply(f_re, f_im, False)
+
+    def rmatvec(self, f_re, f_im):
+        return self._apply(f_re, f_im, True)
+
+
+# --------------------------------------------------------------------------- periodic orbits
+class NekExtVec:
+    """`nek_ext_dvector` (src/vectors/real_extended_vectors.f90): NekVec + period T (dot adds T*T', :243; axpby :193)."""
+
+    def __init__(self, vec: NekVec, T: float = 0.0):
+        self.vec, self.T = vec, float(T)
+
+    def copy(self):
+        return NekExtVec(self.vec.copy(), self.T)
+
+    def scal(self, a):
+        self.vec.scal(a); self.T *= a
+
+    def axpby(self, alpha, other: "NekExtVec", beta):
+        self.vec.axpby(alpha, other.vec, beta); self.T = beta * self.T + alpha * other.T
+
+    def dot(self, other):
+        return self.vec.dot(other.vec) + self.T * other.T
+
+    def norm(self):
+        return math.sqrt(self.dot(self))
+
+
+class UPOJacobian:
+    """`nek_upo_jacobian` (src/systems/periodic_orbit.f90:46-181) with two steppers: `lin` (perturbation) and `nl` (base flow,
+    nonlinear mode), advanced together as Nek does with ifbase: the perturbation step sees the base flow of the previous time
+    level (SURVEY.md call stack), then the base flow moves."""
+
+    def __init__(self, lin, nl, X: NekExtVec):
+        self.lin, self.nl, self.X = lin, nl, X
+
+    def _coupled(self, istep):
+        lin, nl = self.lin, self.nl
+        lin.U = [x.copy() for x in nl.vp]; lin._dirty = True       # CPertStepper pushes base flow + mode on the next advance
+        lin.advance(istep)
+        nl.advance(istep)
+
+    def _fdot(self):                                               # compute_fdot (neklab_systems.f90:202-223)
+        nl = self.nl
+        v0 = [x.copy() for x in nl.vp]; p0 = nl.prp.copy()
+        nl.reset_history()
+        nl.advance(1)
+        out = NekVec(nl.mesh, nl.prm.torder, nl.prm.ifheat)
+        out.v = [(a - b) / nl.dt for a, b in zip(nl.vp, v0)]; out.pr = (nl.prp - p0) / nl.dt
+        return NekExtVec(out, 0.0)
+
+    def _apply(self, vin: NekExtVec, transpose: bool) -> NekExtVec:
+        lin, nl, X = self.lin, self.nl, self.X
+        nrst = lin.prm.torder - 1
+        atol = lin.prm.vtol
+        fac = 0.5 if transpose else 0.1
+        for s in (lin, nl):
+            s.prm.vtol = atol * fac; s.prm.ptol = atol * fac
+            if hasattr(s, "ref"):
+                s.ref.set_params(s.prm, getattr(s, "variant", 0))
+        # base flow := X, dt from its CFL at 0.4 over T_X
+        nl.nonlinear = True; nl.adjoint = False
+        nl.U = [x.copy() for x in X.vec.v]
+        nl.setup(X.T, 0.4, False)
+        nl.set_state(X.vec.v, X.vec.pr, X.vec.theta); nl.reset_history()
+        lin.U = [x.copy() for x in X.vec.v]
+        lin.setup(X.T, 0.4, transpose)
+        lin.set_state(vin.vec.v, vin.vec.pr, vin.vec.theta); lin.reset_history()
+        for istep in range(1, lin.nsteps + 1):
+            self._coupled(istep)
+            if istep <= nrst and vin.vec.nrst > 0:
+                r = vin.vec.get_rst(istep)
+                lin.set_state(r.v, r.pr, r.theta)
+        out = NekVec(lin.mesh, lin.prm.torder, lin.prm.ifheat)
+        out.v = [x.copy() for x in lin.vp]; out.pr = lin.prp.copy(); out.theta = lin.tp.copy()
+        for k in range(1, nrst + 1):
+            self._coupled(lin.nsteps + k)
+            s = NekVec(lin.mesh, lin.prm.torder, lin.prm.ifheat)
+            s.v = [x.copy() for x in lin.vp]; s.pr = lin.prp.copy(); s.theta = lin.tp.copy()
+            out.save_rst(s, k)
+        res = NekExtVec(out, 0.0)
+        res.axpby(-1.0, vin, 1.0)                                  # vec_out%sub(vec_in)
+        res.axpby(vin.T, self._fdot(), 1.0)                        # + f'(X(T)) dT (base flow where the trajectory stands)
+        nl.set_state(X.vec.v, X.vec.pr, X.vec.theta)
+        res.T = vin.dot(self._fdot())                              # phase condition at X(0)
+        for s in (lin, nl):
+            s.prm.vtol = atol; s.prm.ptol = atol
+            if hasattr(s, "ref"):
+                s.ref.set_params(s.prm, getattr(s, "variant", 0))
+        lin.adjoint = False
+        return res
+
+    def matvec(self, vin):
+        return self._apply(vin, False)
+
+    def rmatvec(self, vin):
+        return self._apply(vin, True)
