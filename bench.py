@@ -37,6 +37,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 LAYERS_HEADLINE = 50          # 50 x 1996 = 99 800 elements ("~100k elements")
+# measured DRAM bytes per launch of the roofline kernel (k_axhelm8a<FUSE_CG>), keyed by points per GPU: ncu --set full,
+# profiles/r02_ncu_axhelm8a_headline.md (4.0882 GB read + 0.8055 GB written; algorithmic 4.9054 GB)
+NCU_TRAFFIC_AXHELM8A = {51097600: 4.8938e9}
 
 
 def load_peaks():
@@ -395,11 +398,12 @@ def native_arm(workload, steps, warmup, a, rank, world, local):
         # (p = hd r + beta p on load, p.Ap on the way out); CUDA events on the library stream right after the timed region
         ms_ax, bytes_ax = ctx.bench_kernel(8, 50)
         share = s["cg_iters"] / steps * ms_ax / ms_step
-        roof = {"kernel": "k_axhelm<8,3,FUSE_CG=true> (K1/K8: fused Helmholtz apply of the Jacobi-PCG), timed back-to-back on the step's own buffers",
+        roof = {"kernel": "k_axhelm8a<FUSE_CG=true> (K1/K8: fused Helmholtz apply of the Jacobi-PCG, lx1 = 8, cp.async-staged factors), timed back-to-back on the step's own buffers",
                 "bound": "hbm", "achieved": bytes_ax / (ms_ax * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_ax / (ms_ax * 1e-3) / 1e9 / peak,
-                "traffic": None, "peak_source": peak_src, "us_per_launch": ms_ax * 1e3, "algorithmic_bytes_per_launch": bytes_ax,
+                "traffic": NCU_TRAFFIC_AXHELM8A.get(int(npts)), "peak_source": peak_src, "us_per_launch": ms_ax * 1e3, "algorithmic_bytes_per_launch": bytes_ax,
                 "launches_per_step": s["cg_iters"] / steps, "share_of_step": share,
-                "traffic_note": "see profiles/ for the ncu --set full capture of this kernel (dram bytes / algorithmic)"}
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from one ncu --set full capture at this size "
+                                "(profiles/r02_ncu_axhelm8a_headline.md); null at sizes that were not captured"}
         names = (("axhelm_plain", 0), ("cg_update_reduce", 9), ("dssum", 1), ("dssum3", 12), ("cdabdtp", 2), ("opgradt", 10), ("opdiv", 11), ("convect", 3), ("precond", 4), ("schwarz", 7), ("vec_dot", 5))
         for name, which in names:
             try:

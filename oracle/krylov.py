@@ -180,6 +180,7 @@ def gmres(apply, b, x0, kdim=30, atol=ATOL_DP, rtol=RTOL_DP, maxiter=10):
             r = b.copy(); r.nrst = 0                    # zero initial guess: no matvec (LightKrylov skips it too)
         else:
             r = apply(x); r.axpby(1.0, b, -1.0)         # r = b - A x
+            r.nrst = 0                                  # a restart residual carries no rst fields (same choice as nlk_gmres)
         beta = r.norm()
         if beta < tol:
             break
