@@ -373,7 +373,8 @@ int nlk_ctx_set_forcing(nlk_ctx* c, const double* fx, const double* fy, const do
 int nlk_vec_create(nlk_ctx* c, nlk_vec** out) {
   nlk_vec* v = new nlk_vec(); v->c = c;
   for (int k = 0; k < c->dm.ndim; ++k) if (dev_alloc(c, &v->v[k], c->dm.N1)) return 1;
-  if (dev_alloc(c, &v->pr, c->dm.N2) || dev_alloc(c, &v->theta, c->dm.N1)) return 1;
+  if (dev_alloc(c, &v->pr, c->dm.N2)) return 1;
+  if (c->prm.ifheat && dev_alloc(c, &v->theta, c->dm.N1)) return 1;      // no temperature storage without ifheat (Krylov bases at 100k elements)
   *out = v; return 0;
 }
 int nlk_vec_destroy(nlk_vec* v) {
@@ -393,8 +394,17 @@ int vec_alloc_rst(nlk_vec* v, int s) {
   nlk_ctx* c = v->c;
   if (v->rpr[s]) return 0;
   for (int k = 0; k < c->dm.ndim; ++k) if (dev_alloc(c, &v->rv[s][k], c->dm.N1)) return 1;
-  if (dev_alloc(c, &v->rpr[s], c->dm.N2) || dev_alloc(c, &v->rth[s], c->dm.N1)) return 1;
+  if (dev_alloc(c, &v->rpr[s], c->dm.N2)) return 1;
+  if (c->prm.ifheat && dev_alloc(c, &v->rth[s], c->dm.N1)) return 1;
   return 0;
+}
+void vec_release_rst(nlk_vec* v) {
+  nlk_ctx* c = v->c;
+  if (!v->rpr[0] && !v->rpr[1]) { v->nrst = 0; return; }
+  auto rel = [&](double*& p) { if (!p) return; auto it = std::find(c->allocs.begin(), c->allocs.end(), (void*)p); if (it != c->allocs.end()) { cudaFree(p); c->allocs.erase(it); } p = nullptr; };
+  cudaStreamSynchronize(c->st);
+  for (int s = 0; s < 2; ++s) { for (int k = 0; k < 3; ++k) rel(v->rv[s][k]); rel(v->rpr[s]); rel(v->rth[s]); }
+  v->nrst = 0;
 }
 static int copy_fields(nlk_ctx* c, double* const dv[3], double* dp, double* dt, const double* const sv[3], const double* sp, const double* stt) {
   const DevMesh& dm = c->dm;
@@ -421,7 +431,7 @@ int nlk_vec_zero(nlk_vec* v) {
   nlk_ctx* c = v->c; const DevMesh& dm = c->dm;
   for (int k = 0; k < dm.ndim; ++k) NLK_CUDA(cudaMemsetAsync(v->v[k], 0, dm.N1 * sizeof(double), c->st));
   NLK_CUDA(cudaMemsetAsync(v->pr, 0, dm.N2 * sizeof(double), c->st));
-  NLK_CUDA(cudaMemsetAsync(v->theta, 0, dm.N1 * sizeof(double), c->st));
+  if (v->theta) NLK_CUDA(cudaMemsetAsync(v->theta, 0, dm.N1 * sizeof(double), c->st));
   v->nrst = 0; return 0;
 }
 int nlk_vec_scal(nlk_vec* v, double a) {
@@ -491,7 +501,7 @@ int nlk_vec_upload(nlk_vec* v, const double* vx, const double* vy, const double*
   const double* f[3] = {vx, vy, vz};
   for (int k = 0; k < dm.ndim; ++k) if (f[k]) NLK_CUDA(cudaMemcpyAsync(v->v[k], f[k], dm.N1 * sizeof(double), cudaMemcpyHostToDevice, c->st));
   if (pr) NLK_CUDA(cudaMemcpyAsync(v->pr, pr, dm.N2 * sizeof(double), cudaMemcpyHostToDevice, c->st));
-  if (theta) NLK_CUDA(cudaMemcpyAsync(v->theta, theta, dm.N1 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  if (theta && v->theta) NLK_CUDA(cudaMemcpyAsync(v->theta, theta, dm.N1 * sizeof(double), cudaMemcpyHostToDevice, c->st));
   NLK_CUDA(cudaStreamSynchronize(c->st));
   v->nrst = 0; return 0;
 }
@@ -500,7 +510,8 @@ int nlk_vec_download(const nlk_vec* v, double* vx, double* vy, double* vz, doubl
   double* f[3] = {vx, vy, vz};
   for (int k = 0; k < dm.ndim; ++k) if (f[k]) NLK_CUDA(cudaMemcpyAsync(f[k], v->v[k], dm.N1 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
   if (pr) NLK_CUDA(cudaMemcpyAsync(pr, v->pr, dm.N2 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-  if (theta) NLK_CUDA(cudaMemcpyAsync(theta, v->theta, dm.N1 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  if (theta && v->theta) NLK_CUDA(cudaMemcpyAsync(theta, v->theta, dm.N1 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  else if (theta) std::memset(theta, 0, dm.N1 * sizeof(double));
   NLK_CUDA(cudaStreamSynchronize(c->st));
   return 0;
 }
@@ -573,7 +584,7 @@ namespace nlk {
 static int push_baseflow(nlk_op* op) {            // vec2nek(vx,vy,vz,pr,t, self%baseflow)
   nlk_ctx* c = op->c; const DevMesh& dm = c->dm;
   for (int k = 0; k < dm.ndim; ++k) NLK_CUDA(cudaMemcpyAsync(c->U[k], op->baseflow->v[k], dm.N1 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-  NLK_CUDA(cudaMemcpyAsync(c->T, op->baseflow->theta, dm.N1 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+  if (op->baseflow->theta) NLK_CUDA(cudaMemcpyAsync(c->T, op->baseflow->theta, dm.N1 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
   return 0;
 }
 static int state_from_vec(nlk_ctx* c, const double* const v[3], const double* pr, const double* th) {

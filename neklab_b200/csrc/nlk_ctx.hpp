@@ -170,6 +170,7 @@ int ctx_gs(nlk_ctx* c, Ptr3 f, int nf);                                   // ful
 int ctx_allreduce(nlk_ctx* c, double* d_ptr, int count, bool maxop);
 int ctx_read_scalars(nlk_ctx* c, int count);                              // d_red[0..count) -> h_red, synchronises
 int vec_alloc_rst(nlk_vec* v, int slot);
+void vec_release_rst(nlk_vec* v);                   // free the rst slots (nrst = 0)
 int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose);
 int exptA_project(nlk_op* op, double* const v[3]);
 int step_setup(nlk_ctx* c, double tau, bool transpose);

@@ -151,7 +151,7 @@ int nlk_eigs(nlk_op* op, int32_t nev, int32_t kdim, double tol, int32_t transpos
   if (nev < 1 || kdim < nev + 1) { set_error("eigs: need kdim > nev >= 1"); return 1; }
   if (tol <= 0) tol = std::sqrt(ATOL_DP);
   std::vector<nlk_vec*> X(kdim + 1, nullptr);
-  for (auto& x : X) if (nlk_vec_create(c, &x)) return 1;
+  if (nlk_vec_create(c, &X[0])) return 1;                 // the basis grows with the iteration: at 100k elements a vector is 1.4 GB
   if (x0) { if (nlk_vec_copy(X[0], x0)) return 1; } else { if (nlk_vec_rand(X[0], 0, 12345)) return 1; }
   double nr; if (nlk_vec_norm(X[0], &nr)) return 1;
   if (nr == 0) { set_error("eigs: zero starting vector"); return 1; }
@@ -179,7 +179,12 @@ int nlk_eigs(nlk_op* op, int32_t nev, int32_t kdim, double tol, int32_t transpos
   for (int outer = 0; outer <= maxrestart && conv < nev; ++outer) {
     for (int k = kstart; k < kdim; ++k) {
       // Arnoldi step: X[k+1] = A X[k]; DGS; normalise
+      if (!X[k + 1] && nlk_vec_create(c, &X[k + 1])) return 1;
       if (exptA_apply(op, X[k], X[k + 1], transpose != 0)) return 1;
+      // rst fields are read only from the vector a matvec starts from: with the reference's axpby (rst slots receive the
+      // CURRENT fields of the other vector, real_vectors.f90:186-200) nothing ever reads X[k]'s again -- free them, so that a
+      // basis vector costs d fields + pressure instead of three times that
+      if (c->prm.rst_mode != 1) vec_release_rst(X[k]);
       std::vector<double> h(k + 1);
       if (basis_dgs(c, X[k + 1], X.data(), k + 1, h.data())) return 1;
       for (int i = 0; i <= k; ++i) H[(size_t)i * ldh + k] = h[i];
@@ -344,6 +349,7 @@ int nlk_gmres(nlk_op* op, int32_t minus_identity, const nlk_vec* b, nlk_vec* x, 
     g[0] = beta; int kk = 0;
     for (int k = 0; k < kdim; ++k) {
       if (apply(V[k], V[k + 1])) return 1;
+      if (c->prm.rst_mode != 1) vec_release_rst(V[k]);            // as in nlk_eigs: only the newest vector's rst fields are ever read
       std::vector<double> h(k + 1);
       if (basis_dgs(c, V[k + 1], V.data(), k + 1, h.data())) return 1;
       double hn; if (nlk_vec_norm(V[k + 1], &hn)) return 1;
