@@ -212,6 +212,15 @@ module nlk_c
          import; type(c_ptr), value :: op, b, x; integer(c_int32_t), value :: minus_identity, kdim, maxiter, transpose
          real(c_double), value :: atol, rtol; integer(c_int32_t), intent(out) :: info
       end function
+      ! resolvent_linop (src/linops/resolvent.f90) and nek_upo_jacobian (src/systems/periodic_orbit.f90)
+      integer(c_int) function nlk_resolvent_matvec(op, omega, f_re, f_im, out_re, out_im, adjoint, rtol, info) bind(C, name="nlk_resolvent_matvec")
+         import; type(c_ptr), value :: op, f_re, f_im, out_re, out_im; real(c_double), value :: omega, rtol
+         integer(c_int32_t), value :: adjoint; integer(c_int32_t), intent(out) :: info
+      end function
+      integer(c_int) function nlk_upo_jacobian(ctx, X, T_X, vin, T_in, vout, T_out, transpose) bind(C, name="nlk_upo_jacobian")
+         import; type(c_ptr), value :: ctx, X, vin, vout; real(c_double), value :: T_X, T_in; real(c_double), intent(out) :: T_out
+         integer(c_int32_t), value :: transpose
+      end function
    end interface
 end module nlk_c
 

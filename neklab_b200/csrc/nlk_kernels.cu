@@ -240,8 +240,12 @@ __device__ __forceinline__ void cp_async_wait_le(int pending) {      // wait unt
     default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
   }
 }
-template <bool FUSE_CG>
-__global__ void __launch_bounds__(128, 4)
+// REGD: the four rows/columns of D a thread needs (D[i][.], D[j][.], D[.][i], D[.][j]) live in registers for the whole k-loop,
+// so that a contraction FMA costs ONE shared-memory operand instead of two.  ncu r02 (after the cp.async staging): the LSU
+// data pipe of this kernel ran at 64 % of its peak (1 913 shared-memory wavefronts per element), short scoreboard + MIO
+// throttle = 56 % of the stall samples -- operand delivery, not DRAM, was what kept it at 67 % of the HBM roof.
+template <bool FUSE_CG, bool REGD>
+__global__ void __launch_bounds__(128, REGD ? 3 : 4)
 k_axhelm8a(const double* __restrict__ u, double* __restrict__ pio, const double* __restrict__ r, double* __restrict__ w,
            const double* __restrict__ G, const double* __restrict__ bm1, const double* __restrict__ Dg,
            const double* __restrict__ hd, double h1, double h2,
@@ -292,6 +296,12 @@ k_axhelm8a(const double* __restrict__ u, double* __restrict__ pio, const double*
 #pragma unroll
   for (int k = 0; k < NZ; ++k) rw[k] = 0.0;
   const double* sGe = sG + (size_t)le * NG * NP + tid;
+  double dI[N], dJ[N], tI[N], tJ[N];                        // D[i][l], D[j][l], D[l][i], D[l][j]
+  if (REGD) {
+    __syncthreads();                                        // sD / sDt written above
+#pragma unroll
+    for (int l = 0; l < N; ++l) { dI[l] = sD[i * N + l]; dJ[l] = sD[j * N + l]; tI[l] = sDt[i * N + l]; tJ[l] = sDt[j * N + l]; }
+  }
 #pragma unroll
   for (int k = 0; k < NZ; ++k) {
     s_u[le][tid] = ru[k];
@@ -303,8 +313,8 @@ k_axhelm8a(const double* __restrict__ u, double* __restrict__ pio, const double*
     double ur = 0, us = 0, ut = 0;
 #pragma unroll
     for (int l = 0; l < N; ++l) {
-      ur += sDt[l * N + i] * s_u[le][j * N + l];
-      us += sD[j * N + l] * s_u[le][l * N + i];
+      ur += (REGD ? dI[l] : sDt[l * N + i]) * s_u[le][j * N + l];
+      us += (REGD ? dJ[l] : sD[j * N + l]) * s_u[le][l * N + i];
     }
 #pragma unroll
     for (int l = 0; l < N; ++l) ut += c_D[k * N + l] * ru[l];
@@ -315,7 +325,7 @@ k_axhelm8a(const double* __restrict__ u, double* __restrict__ pio, const double*
     __syncthreads();
     double acc = 0;
 #pragma unroll
-    for (int l = 0; l < N; ++l) acc += sD[l * N + i] * s_gr[le][j * N + l] + sD[l * N + j] * s_gs[le][l * N + i];
+    for (int l = 0; l < N; ++l) acc += (REGD ? tI[l] : sD[l * N + i]) * s_gr[le][j * N + l] + (REGD ? tJ[l] : sD[l * N + j]) * s_gs[le][l * N + i];
     rw[k] += acc;
 #pragma unroll
     for (int l = 0; l < N; ++l) rw[l] += c_D[k * N + l] * gt;
@@ -366,9 +376,19 @@ static void axhelm_dispatch(const DevMesh& dm, const double* u, double* pio, con
     if (!no_async) {
       constexpr size_t smem = (size_t)EPB * 6 * 512 * sizeof(double);
       static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(k_axhelm8a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaFuncSetAttribute(k_axhelm8a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-      if (fuse) k_axhelm8a<true><<<grid, block, smem, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, hd, h1, h2, sc, dm.E, pap_partial, pap_counter, defer);
-      else k_axhelm8a<false><<<grid, block, smem, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, nullptr, h1, h2, nullptr, dm.E, nullptr, nullptr, 0);
+      static const bool lds_d = getenv("NLK_AX8_LDSD") != nullptr;      // A/B switch: D operands from shared memory (the r02 first version)
+      if (!attr) {
+        cudaFuncSetAttribute(k_axhelm8a<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaFuncSetAttribute(k_axhelm8a<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_axhelm8a<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cudaFuncSetAttribute(k_axhelm8a<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+      }
+      if (lds_d) {
+        if (fuse) k_axhelm8a<true, false><<<grid, block, smem, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, hd, h1, h2, sc, dm.E, pap_partial, pap_counter, defer);
+        else k_axhelm8a<false, false><<<grid, block, smem, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, nullptr, h1, h2, nullptr, dm.E, nullptr, nullptr, 0);
+      } else {
+        if (fuse) k_axhelm8a<true, true><<<grid, block, smem, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, hd, h1, h2, sc, dm.E, pap_partial, pap_counter, defer);
+        else k_axhelm8a<false, true><<<grid, block, smem, st>>>(u, pio, r, w, dm.G, dm.bm1, dm.D, nullptr, h1, h2, nullptr, dm.E, nullptr, nullptr, 0);
+      }
       LAUNCH_COUNT(); return;
     }
   }
