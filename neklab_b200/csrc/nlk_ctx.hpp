@@ -181,7 +181,7 @@ int cg_weights(nlk_ctx* c, const double* mask, double h1, double h2, int* slot_o
 // fused Schwarz branch of the pressure preconditioner (nlk_schwarz.cu)
 int swf_setup(nlk_ctx* c);
 void swf_release(nlk_ctx* c);
-int swf_apply(nlk_ctx* c, const double* r, const double* in_mul, const double* yc, double* z, cudaEvent_t wait_before_b = nullptr);
+int swf_apply(nlk_ctx* c, const double* r, const double* in_mul, const double* yc, double* z, cudaEvent_t wait_before_b = nullptr, int phase = 0);   // phase 1: kernel A (+ exchanges) only, 2: kernel B only
 int helmholtz_solve_multi(nlk_ctx* c, int nf, double* const* rhs_local, double h1, double h2, const double* const* masks, double tol, double* const* sol);
 int sync_cg_counter(nlk_ctx* c);
 int pressure_solve(nlk_ctx* c, const double* rhs, double tol, double* x, int* iters);

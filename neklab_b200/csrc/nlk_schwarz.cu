@@ -101,14 +101,18 @@ static int swf_exchange(nlk_ctx* c, SwfState& S, double* ghost) {
 }
 
 // the Schwarz branch alone: z = W sum_e R_e^T FDM_e R_e (in_mul r) [+ prolong(yc) when yc != nullptr]
-int swf_apply(nlk_ctx* c, const double* r, const double* in_mul, const double* yc, double* z, cudaEvent_t wait_before_b) {
+int swf_apply(nlk_ctx* c, const double* r, const double* in_mul, const double* yc, double* z, cudaEvent_t wait_before_b, int phase) {
   SwfState& S = *static_cast<SwfState*>(c->swf);
   const DevMesh& dm = c->dm;
-  if (S.nghost > 0) { launch_swf_pack(r, in_mul, S.send_inner, S.nghost, S.sendbuf, c->st); if (swf_exchange(c, S, S.ghostA)) return 1; }
-  if (!tp_swf_a(dm, r, in_mul, S.t1, S.ghostA, S.zint, S.ZF, c->st)) { set_error("fused Schwarz: no kernel instantiation for this lx1"); return 1; }
-  if (S.nghost > 0) { launch_swf_pack(S.ZF, nullptr, S.send_face, S.nghost, S.sendbuf, c->st); if (swf_exchange(c, S, S.ghostB)) return 1; }
-  if (wait_before_b) NLK_CUDA(cudaStreamWaitEvent(c->st, wait_before_b, 0));
-  tp_swf_b(dm, S.zint, S.ZF, S.t2, S.ghostB, yc, z, c->st);
+  if (phase != 2) {
+    if (S.nghost > 0) { launch_swf_pack(r, in_mul, S.send_inner, S.nghost, S.sendbuf, c->st); if (swf_exchange(c, S, S.ghostA)) return 1; }
+    if (!tp_swf_a(dm, r, in_mul, S.t1, S.ghostA, S.zint, S.ZF, c->st)) { set_error("fused Schwarz: no kernel instantiation for this lx1"); return 1; }
+    if (S.nghost > 0) { launch_swf_pack(S.ZF, nullptr, S.send_face, S.nghost, S.sendbuf, c->st); if (swf_exchange(c, S, S.ghostB)) return 1; }
+  }
+  if (phase != 1) {
+    if (wait_before_b) NLK_CUDA(cudaStreamWaitEvent(c->st, wait_before_b, 0));
+    tp_swf_b(dm, S.zint, S.ZF, S.t2, S.ghostB, yc, z, c->st);
+  }
   return 0;
 }
 

@@ -203,14 +203,17 @@ int apply_precond(nlk_ctx* c, const double* r, double* z, const double* in_mul) 
       launch_gemv(dm.A0inv, c->crs_r, c->crs_y, (int)dm.nvert, c->st);
       return 0;
     };
+    static const bool swf_first = getenv("NLK_SWF_FIRST") != nullptr;      // A/B: enqueue the Schwarz kernel before the coarse chain
     if (side) {
       NLK_CUDA(cudaEventRecord(c->ev_in, c->st));
       NLK_CUDA(cudaStreamWaitEvent(c->st2, c->ev_in, 0));
+      if (swf_first && swf_apply(c, r, in_mul, nullptr, z, nullptr, 1)) return 1;
       cudaStream_t main_st = c->st; c->st = c->st2;
       int rc = coarse_chain();
       c->st = main_st;
       if (rc) return 1;
       NLK_CUDA(cudaEventRecord(c->ev_crs, c->st2));
+      if (swf_first) return swf_apply(c, r, in_mul, c->crs_y, z, c->ev_crs, 2);
     } else if (c->have_coarse) { if (coarse_chain()) return 1; }
     return swf_apply(c, r, in_mul, c->have_coarse ? c->crs_y : nullptr, z, side ? c->ev_crs : nullptr);    // kernel B waits for the coarse solve
   }
