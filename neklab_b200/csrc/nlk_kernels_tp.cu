@@ -222,8 +222,8 @@ __device__ __forceinline__ void group_sync(int id, int nthreads) { asm volatile(
 
 // Component-parallel layout: warp group g (P threads, named barrier g+1) carries velocity component g through all three
 // sum-factorisation stages on its own shared-memory tiles; the three partial divergences are summed at the end.
-template <int N>
-__global__ void __launch_bounds__(3 * roundup32(N * N))
+template <int N, int MINB>
+__global__ void __launch_bounds__(3 * roundup32(N * N), MINB)
 k_opdiv3_t(CPtr3 u, double* __restrict__ p, const double* __restrict__ rxw2, double scale, const double* __restrict__ in_mul, CPtr3 in_mask,
            const double* __restrict__ out_mul) {
   constexpr int n = N, q = N - 2, np1 = n * n * n, np2 = q * q * q, P = roundup32(n * n);
@@ -333,8 +333,8 @@ k_opdiv3_t(CPtr3 u, double* __restrict__ p, const double* __restrict__ rxw2, dou
 }
 
 // Component-parallel: warp group g produces w_g = D_g^T p.
-template <int N>
-__global__ void __launch_bounds__(3 * roundup32(N * N))
+template <int N, int MINB>
+__global__ void __launch_bounds__(3 * roundup32(N * N), MINB)
 k_opgradt3_t(const double* __restrict__ p, Ptr3 w, const double* __restrict__ rxw2) {
   constexpr int n = N, q = N - 2, np1 = n * n * n, np2 = q * q * q, P = roundup32(n * n);
   constexpr int npad = n | 1, qp = q | 1;
@@ -428,7 +428,7 @@ k_opgradt3_t(const double* __restrict__ p, Ptr3 w, const double* __restrict__ rx
 
 // ------------------------------------------------------------------------------------------------ K3 convect
 template <int N, int MD, int DIM>
-__global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __restrict__ rxd, const double* __restrict__ I1dg,
+__device__ __forceinline__ void convect_t_body(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __restrict__ rxd, const double* __restrict__ I1dg,
                             const double* __restrict__ I1dtg, const double* __restrict__ Ddg, double alpha, int accumulate) {
   constexpr int n = N, m = MD, d = DIM, nz = DIM == 3 ? N : 1, mz = DIM == 3 ? MD : 1;
   constexpr int np1 = n * n * nz, npd = m * m * mz;
@@ -532,6 +532,19 @@ __global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __
     for (int i = threadIdx.x; i < np1; i += blockDim.x) of[i] = (accumulate ? of[i] : 0.0) + alpha * W2[(i % n) + PN * (i / n)];
     __syncthreads();
   }
+}
+
+template <int N, int MD, int DIM>
+__global__ void k_convect_t(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __restrict__ rxd, const double* __restrict__ I1dg,
+                            const double* __restrict__ I1dtg, const double* __restrict__ Ddg, double alpha, int accumulate) {
+  convect_t_body<N, MD, DIM>(u, nf, C, out, rxd, I1dg, I1dtg, Ddg, alpha, accumulate);
+}
+// the same body under explicit launch bounds (A/B: NLK_CONVECT_LB=1|2 -> minBlocks 1|2)
+template <int N, int MD, int DIM, int MINB>
+__global__ void __launch_bounds__(tp_block_threads(MD), MINB)
+k_convect_tb(CPtr4 u, int nf, CPtr3 C, Ptr4 out, const double* __restrict__ rxd, const double* __restrict__ I1dg,
+             const double* __restrict__ I1dtg, const double* __restrict__ Ddg, double alpha, int accumulate) {
+  convect_t_body<N, MD, DIM>(u, nf, C, out, rxd, I1dg, I1dtg, Ddg, alpha, accumulate);
 }
 
 // ------------------------------------------------------------------------------------------------ K4 convect_adj
@@ -749,7 +762,8 @@ __global__ void k_swf_b(const double* __restrict__ zint, const double* __restric
 // whole contraction and the data as one 8-byte shared-memory load per lane and 256 FMAs: 16 DMMA + 16 LDS + 16 STS per
 // contraction and warp instead of ~1 000 LDS.  FP64 has no tcgen05 path; DMMA is the FP64 tensor pipe of sm_100a.
 constexpr int SWF8_WARPS = 4;
-__global__ void __launch_bounds__(32 * SWF8_WARPS)
+template <int MINB>
+__global__ void __launch_bounds__(32 * SWF8_WARPS, MINB)
 k_swf_a8(const double* __restrict__ r, const double* __restrict__ mul, const int32_t* __restrict__ t1, const double* __restrict__ ghost,
          const double* __restrict__ S, const double* __restrict__ St, const double* __restrict__ dinv,
          double* __restrict__ zint, double* __restrict__ ZF, int64_t E) {
@@ -855,7 +869,14 @@ bool tp_opdiv(const DevMesh& dm, CPtr3 u, double* p, double scale, const double*
     const int n = dm.n, q = dm.q;
     size_t sm3 = (size_t)(3 * ((n | 1) * n * n + 2 * (q | 1) * n * n + 2 * q * q * n) + 3 * q * q * q) * sizeof(double);
     int thr3 = 3 * roundup32(n * n);
-#define FN3(N_) case N_: { static bool s_ = false; if (!s_) { set_smem(k_opdiv3_t<N_>, sm3); s_ = true; } k_opdiv3_t<N_><<<(unsigned)dm.E, thr3, sm3, st>>>(u, p, dm.rxw2, scale, in_mul, mk, out_mul); ++g_launches; return true; }
+    // minBlocks = 1 in __launch_bounds__ (108 registers instead of 110, same 3 blocks per SM, different instruction schedule):
+    // 313.5 -> 244.1 us at 24k elements, measured A/B in one run (NLK_OPDIV_MINB0=1 selects the old code)
+    static const int minb0 = getenv("NLK_OPDIV_MINB0") != nullptr;
+    static const int minb4 = getenv("NLK_OPDIV_MINB4") != nullptr;      // A/B: cap the registers so that four blocks fit an SM
+#define FN3(N_) case N_: { static bool s_ = false; if (!s_) { set_smem(k_opdiv3_t<N_, 1>, sm3); set_smem(k_opdiv3_t<N_, 4>, sm3); set_smem(k_opdiv3_t<N_, 0>, sm3); s_ = true; } \
+      if (minb4) k_opdiv3_t<N_, 4><<<(unsigned)dm.E, thr3, sm3, st>>>(u, p, dm.rxw2, scale, in_mul, mk, out_mul); \
+      else if (minb0) k_opdiv3_t<N_, 0><<<(unsigned)dm.E, thr3, sm3, st>>>(u, p, dm.rxw2, scale, in_mul, mk, out_mul); \
+      else k_opdiv3_t<N_, 1><<<(unsigned)dm.E, thr3, sm3, st>>>(u, p, dm.rxw2, scale, in_mul, mk, out_mul); ++g_launches; return true; }
     switch (n) { FN3(4) FN3(5) FN3(6) FN3(7) FN3(8) FN3(9) FN3(10) default: break; }
 #undef FN3
   }
@@ -873,7 +894,9 @@ bool tp_opgradt(const DevMesh& dm, const double* p, Ptr3 w, cudaStream_t st) {
     const int n = dm.n, q = dm.q;
     size_t sm3 = (size_t)(3 * (3 * (q | 1) * q * q + 3 * (n | 1) * q * q + 2 * n * n * q)) * sizeof(double);
     int thr3 = 3 * roundup32(n * n);
-#define FN3(N_) case N_: { static bool s_ = false; if (!s_) { set_smem(k_opgradt3_t<N_>, sm3); s_ = true; } k_opgradt3_t<N_><<<(unsigned)dm.E, thr3, sm3, st>>>(p, w, dm.rxw2); ++g_launches; return true; }
+    static const int gminb1 = getenv("NLK_OPGRADT_MINB0") == nullptr;     // minBlocks = 1 changes ptxas' schedule: 188.6 -> 182.4 us at 24k elements (A/B: NLK_OPGRADT_MINB0=1)
+#define FN3(N_) case N_: { static bool s_ = false; if (!s_) { set_smem(k_opgradt3_t<N_, 0>, sm3); set_smem(k_opgradt3_t<N_, 1>, sm3); s_ = true; } \
+      if (gminb1) k_opgradt3_t<N_, 1><<<(unsigned)dm.E, thr3, sm3, st>>>(p, w, dm.rxw2); else k_opgradt3_t<N_, 0><<<(unsigned)dm.E, thr3, sm3, st>>>(p, w, dm.rxw2); ++g_launches; return true; }
     switch (n) { FN3(4) FN3(5) FN3(6) FN3(7) FN3(8) FN3(9) FN3(10) default: break; }
 #undef FN3
   }
@@ -907,6 +930,13 @@ bool tp_convect(const DevMesh& dm, CPtr4 u, int nf, CPtr3 C, Ptr4 out, double al
   if (smem > 220 * 1024) return false;
   ensure_const_ops(dm, st);
   int thr = tp_threads(dm.m, dm.ndim, dm.npd);
+  static const int lb = getenv("NLK_CONVECT_LB") ? atoi(getenv("NLK_CONVECT_LB")) : 1;      // 2214 -> 2147 us at 24k elements with (160, 1); 0 = no launch bounds
+  if (dm.n == 8 && dm.m == 12 && dm.ndim == 3 && lb > 0 && thr == tp_block_threads(12)) {          // headline shape only: launch-bounds variants
+    static bool s_ = false; if (!s_) { set_smem(k_convect_tb<8, 12, 3, 1>, smem); set_smem(k_convect_tb<8, 12, 3, 2>, smem); s_ = true; }
+    if (lb == 1) k_convect_tb<8, 12, 3, 1><<<(unsigned)dm.E, thr, smem, st>>>(u, nf, C, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, alpha, accumulate);
+    else k_convect_tb<8, 12, 3, 2><<<(unsigned)dm.E, thr, smem, st>>>(u, nf, C, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, alpha, accumulate);
+    ++g_launches; return true;
+  }
 #define FN(N_, M_, D_) { static bool s_ = false; if (!s_) { set_smem(k_convect_t<N_, M_, D_>, smem); s_ = true; } k_convect_t<N_, M_, D_><<<(unsigned)dm.E, thr, smem, st>>>(u, nf, C, out, dm.rxd, dm.I1d, dm.I1dt, dm.Dd, alpha, accumulate); }
   TP_SWITCH_NM((dm.n * 100 + dm.m) * 10 + dm.ndim)
 #undef FN
@@ -926,7 +956,11 @@ bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha,
 bool tp_swf_a(const DevMesh& dm, const double* r, const double* mul, const int32_t* t1, const double* ghost, double* zint, double* ZF, cudaStream_t st) {
   static const bool no_dmma = getenv("NLK_NO_DMMA") != nullptr;
   if (dm.n == 8 && dm.ndim == 3 && !no_dmma) {            // FP64 tensor-core path, one warp per element
-    k_swf_a8<<<(unsigned)((dm.E + SWF8_WARPS - 1) / SWF8_WARPS), 32 * SWF8_WARPS, 0, st>>>(r, mul, t1, ghost, dm.fdmS, dm.fdmSt, dm.fdmDinv, zint, ZF, dm.E);
+    static const int minb = getenv("NLK_SWF8_MINB") ? atoi(getenv("NLK_SWF8_MINB")) : 6;      // 80 registers -> 6 blocks (24 warps) per SM: 265 -> 241 us at 24k elements (1: 104 registers, 4 blocks)
+    const unsigned g8 = (unsigned)((dm.E + SWF8_WARPS - 1) / SWF8_WARPS);
+    if (minb == 6) k_swf_a8<6><<<g8, 32 * SWF8_WARPS, 0, st>>>(r, mul, t1, ghost, dm.fdmS, dm.fdmSt, dm.fdmDinv, zint, ZF, dm.E);
+    else if (minb == 5) k_swf_a8<5><<<g8, 32 * SWF8_WARPS, 0, st>>>(r, mul, t1, ghost, dm.fdmS, dm.fdmSt, dm.fdmDinv, zint, ZF, dm.E);
+    else k_swf_a8<1><<<g8, 32 * SWF8_WARPS, 0, st>>>(r, mul, t1, ghost, dm.fdmS, dm.fdmSt, dm.fdmDinv, zint, ZF, dm.E);
     ++g_launches; return true;
   }
   const size_t npP = dm.ndim == 3 ? (size_t)(dm.n | 1) * dm.n * dm.n : (size_t)dm.np1;
