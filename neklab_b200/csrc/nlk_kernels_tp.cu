@@ -956,7 +956,7 @@ bool tp_convect_adj(const DevMesh& dm, CPtr3 U, CPtr3 c, Ptr3 out, double alpha,
 bool tp_swf_a(const DevMesh& dm, const double* r, const double* mul, const int32_t* t1, const double* ghost, double* zint, double* ZF, cudaStream_t st) {
   static const bool no_dmma = getenv("NLK_NO_DMMA") != nullptr;
   if (dm.n == 8 && dm.ndim == 3 && !no_dmma) {            // FP64 tensor-core path, one warp per element
-    static const int minb = getenv("NLK_SWF8_MINB") ? atoi(getenv("NLK_SWF8_MINB")) : 6;      // 80 registers -> 6 blocks (24 warps) per SM: 265 -> 241 us at 24k elements (1: 104 registers, 4 blocks)
+    static const int minb = getenv("NLK_SWF8_MINB") ? atoi(getenv("NLK_SWF8_MINB")) : 1;      // 6 (80 registers, 24 warps per SM) runs the branch ALONE 9 % faster (265 -> 241 us at 24k elements) but leaves the side-stream coarse chain no room: whole preconditioner 1576 -> 1659 us at 99 800 elements
     const unsigned g8 = (unsigned)((dm.E + SWF8_WARPS - 1) / SWF8_WARPS);
     if (minb == 6) k_swf_a8<6><<<g8, 32 * SWF8_WARPS, 0, st>>>(r, mul, t1, ghost, dm.fdmS, dm.fdmSt, dm.fdmDinv, zint, ZF, dm.E);
     else if (minb == 5) k_swf_a8<5><<<g8, 32 * SWF8_WARPS, 0, st>>>(r, mul, t1, ghost, dm.fdmS, dm.fdmSt, dm.fdmDinv, zint, ZF, dm.E);
