@@ -222,7 +222,7 @@ class Context:
 
     def set_tol(self, vtol, ptol):
         _chk(lib().nlk_ctx_set_tol(self.h, C.c_double(vtol), C.c_double(ptol)))
-        self.params.vtol = vtol; self.params.ptol = ptol
+        self.params.vtol = vtol; self.params.ptol = ptol; self.params.ttol = vtol
 
     def set_dt(self, dt):
         _chk(lib().nlk_ctx_set_dt(self.h, C.c_double(dt)))

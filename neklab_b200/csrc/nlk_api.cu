@@ -330,7 +330,9 @@ int nlk_ctx_destroy(nlk_ctx* c) {
   delete c->bank2;
   delete c; return 0;
 }
-int nlk_ctx_set_tol(nlk_ctx* c, double vtol, double ptol) { c->prm.vtol = vtol; c->prm.ptol = ptol; return 0; }
+// setup_nek(vtol=, ptol=) (src/neklab_nek_setup.f90:226-230): param(22) = vtol also becomes restol(:) / atol(:) of EVERY field, so the
+// temperature Helmholtz tolerance follows the velocity one
+int nlk_ctx_set_tol(nlk_ctx* c, double vtol, double ptol) { c->prm.vtol = vtol; c->prm.ptol = ptol; c->prm.ttol = vtol; return 0; }
 int nlk_ctx_set_dt(nlk_ctx* c, double dt) { if (dt <= 0) { set_error("dt must be positive"); return 1; } c->dt = dt; return 0; }
 int nlk_ctx_sync(nlk_ctx* c) { NLK_CUDA(cudaStreamSynchronize(c->st)); NLK_CUDA(cudaGetLastError()); return 0; }
 void* nlk_ctx_stream(nlk_ctx* c) { return (void*)c->st; }
@@ -598,13 +600,18 @@ int exptA_project(nlk_op* op, double* const v[3]) {
     launch_planar_proj(v[k], dm.bm1, op->proj_cv, op->proj_sv, op->proj_off, op->proj_idx, op->proj_gid, op->proj_ngroups, dm.N1, op->proj_coef, c->st);
   return 0;
 }
+struct EvPair {            // timing events released on every return path
+  cudaEvent_t a = nullptr, b = nullptr;
+  EvPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~EvPair() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
 // exptA_matvec / exptA_rmatvec (src/linops/exponential_propagator.f90:15-107) incl. get_rst / compute_rst (:109-142)
 int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose) {
   nlk_ctx* c = op->c;
   if (in == out) { set_error("exptA: vec_in and vec_out must differ"); return 1; }
   const int nrst = c->prm.torder - 1;
   if (sync_cg_counter(c)) return 1;
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  EvPair ev; cudaEvent_t e0 = ev.a, e1 = ev.b;
   long l0 = g_launches; long cg0 = c->cg_iters, gm0 = c->gmres_iters, st0 = c->steps;
   cudaEventRecord(e0, c->st);
   if (push_baseflow(op)) return 1;
@@ -632,7 +639,7 @@ int exptA_apply(nlk_op* op, const nlk_vec* in, nlk_vec* out, bool transpose) {
   cudaEventRecord(e1, c->st);
   NLK_CUDA(cudaStreamSynchronize(c->st));
   if (sync_cg_counter(c)) return 1;
-  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   op->stats.nsteps = c->nsteps; op->stats.dt = c->dt; op->stats.ms_total = ms; op->stats.launches = g_launches - l0;
   op->stats.cg_iters = c->cg_iters - cg0; op->stats.gmres_iters = c->gmres_iters - gm0; op->stats.steps = c->steps - st0; op->stats.matvecs += 1;
   return 0;
@@ -742,14 +749,14 @@ int nlk_exptA_time_steps(nlk_op* op, const nlk_vec* in, int32_t nwarm, int32_t n
   if (reset_history_pub(c)) return 1;
   for (int i = 1; i <= nwarm; ++i) if (step_advance(c, i)) return 1;
   if (sync_cg_counter(c)) return 1;
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  EvPair ev; cudaEvent_t e0 = ev.a, e1 = ev.b;
   long l0 = g_launches; long cg0 = c->cg_iters, gm0 = c->gmres_iters, st0 = c->steps;
   cudaEventRecord(e0, c->st);
   for (int i = nwarm + 1; i <= nwarm + nsteps; ++i) if (step_advance(c, i)) return 1;
   cudaEventRecord(e1, c->st);
   NLK_CUDA(cudaStreamSynchronize(c->st));
   if (sync_cg_counter(c)) return 1;
-  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   *ms_timed = ms;
   op->stats.nsteps = c->nsteps; op->stats.dt = c->dt; op->stats.ms_total = ms; op->stats.launches = g_launches - l0;
   op->stats.cg_iters = c->cg_iters - cg0; op->stats.gmres_iters = c->gmres_iters - gm0; op->stats.steps = c->steps - st0;
@@ -976,7 +983,7 @@ int nlk_test_cfl(nlk_ctx* c, const double* ux, const double* uy, const double* u
 
 int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_launch, double* algo_bytes) {
   const DevMesh& dm = c->dm; const int d = dm.ndim;
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  EvPair ev; cudaEvent_t e0 = ev.a, e1 = ev.b;
   auto run = [&]() -> int {
     switch (which) {
       case 0: launch_axhelm(dm, c->wk[0], c->wk[1], 1.0, 1.0, c->st); break;
@@ -1012,7 +1019,7 @@ int nlk_bench_kernel(nlk_ctx* c, int32_t which, int32_t nrep, double* ms_per_lau
   for (int i = 0; i < nrep; ++i) if (run()) return 1;
   cudaEventRecord(e1, c->st);
   NLK_CUDA(cudaStreamSynchronize(c->st));
-  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   *ms_per_launch = ms / nrep;
   double N1 = (double)dm.N1, N2 = (double)dm.N2;
   double bytes = 0;

@@ -130,6 +130,15 @@ static int basis_dgs(nlk_ctx* c, nlk_vec* y, nlk_vec* const* X, int k, double* h
 
 static const double ATOL_DP = 1e-15;
 
+// owns the work vectors of a Krylov driver: every early `return 1` releases them (a retrying caller -- Newton -- must not grow HBM)
+struct VecGuard {
+  std::vector<std::vector<nlk_vec*>*> lists; std::vector<nlk_vec**> singles;
+  ~VecGuard() {
+    for (auto* l : lists) for (auto& x : *l) { nlk_vec_destroy(x); x = nullptr; }
+    for (auto** p : singles) { nlk_vec_destroy(*p); *p = nullptr; }
+  }
+};
+
 }  // namespace nlk
 
 extern "C" {
@@ -151,6 +160,7 @@ int nlk_eigs(nlk_op* op, int32_t nev, int32_t kdim, double tol, int32_t transpos
   if (nev < 1 || kdim < nev + 1) { set_error("eigs: need kdim > nev >= 1"); return 1; }
   if (tol <= 0) tol = std::sqrt(ATOL_DP);
   std::vector<nlk_vec*> X(kdim + 1, nullptr);
+  VecGuard guard; guard.lists.push_back(&X);
   if (nlk_vec_create(c, &X[0])) return 1;                 // the basis grows with the iteration: at 100k elements a vector is 1.4 GB
   if (x0) { if (nlk_vec_copy(X[0], x0)) return 1; } else { if (nlk_vec_rand(X[0], 0, 12345)) return 1; }
   double nr; if (nlk_vec_norm(X[0], &nr)) return 1;
@@ -228,10 +238,10 @@ int nlk_eigs(nlk_op* op, int32_t nev, int32_t kdim, double tol, int32_t transpos
     for (int j = 0; j < p; ++j) brow[j] = H[(size_t)k * ldh + (k - 1)] * Q[j][k - 1];
     // X[:p] <- X[:k] Q (LightKrylov linear_combination = zero + axpby, so rst follows the axpby quirk: nrst = 0 after zero)
     std::vector<nlk_vec*> NX(p, nullptr);
+    VecGuard gnx; gnx.lists.push_back(&NX);
     for (int j = 0; j < p; ++j) { if (nlk_vec_create(c, &NX[j])) return 1; if (nlk_vec_zero(NX[j])) return 1; if (basis_axpy(c, NX[j], X.data(), k, Q[j].data())) return 1; }
     for (int j = 0; j < p; ++j) { std::swap(X[j], NX[j]); }
     std::swap(X[p], X[k]);
-    for (int j = 0; j < p; ++j) nlk_vec_destroy(NX[j]);
     std::fill(H.begin(), H.end(), 0.0);
     for (int a = 0; a < p; ++a) for (int j = 0; j < p; ++j) H[(size_t)a * ldh + j] = T[(size_t)a * p + j];
     for (int j = 0; j < p; ++j) H[(size_t)p * ldh + j] = brow[j];
@@ -252,7 +262,6 @@ int nlk_eigs(nlk_op* op, int32_t nev, int32_t kdim, double tol, int32_t transpos
     }
   }
   if (niter_out) *niter_out = niter;
-  for (auto& x : X) nlk_vec_destroy(x);
   return 0;
 }
 
@@ -263,6 +272,7 @@ int nlk_svds(nlk_op* op, int32_t nsv, int32_t kdim, double tol, const nlk_vec* x
   nlk_ctx* c = op->c;
   if (tol <= 0) tol = std::sqrt(ATOL_DP);
   std::vector<nlk_vec*> U(kdim, nullptr), V(kdim + 1, nullptr);
+  VecGuard guard; guard.lists.push_back(&U); guard.lists.push_back(&V);
   for (auto& x : U) if (nlk_vec_create(c, &x)) return 1;
   for (auto& x : V) if (nlk_vec_create(c, &x)) return 1;
   if (x0) { if (nlk_vec_copy(V[0], x0)) return 1; } else { if (nlk_vec_rand(V[0], 0, 12345)) return 1; }
@@ -312,8 +322,6 @@ int nlk_svds(nlk_op* op, int32_t nsv, int32_t kdim, double tol, const nlk_vec* x
   }
   if (niter_out) *niter_out = n;
   if (conv < nsv) *info = 1;
-  for (auto& x : U) nlk_vec_destroy(x);
-  for (auto& x : V) nlk_vec_destroy(x);
   return 0;
 }
 
@@ -322,8 +330,9 @@ int nlk_gmres(nlk_op* op, int32_t minus_identity, const nlk_vec* b, nlk_vec* x, 
               int32_t transpose, int32_t* info) {
   nlk_ctx* c = op->c;
   std::vector<nlk_vec*> V(kdim + 1, nullptr);
-  for (auto& v : V) if (nlk_vec_create(c, &v)) return 1;
-  nlk_vec* r = nullptr; if (nlk_vec_create(c, &r)) return 1;
+  nlk_vec* r = nullptr;
+  VecGuard guard; guard.lists.push_back(&V); guard.singles.push_back(&r);
+  if (nlk_vec_create(c, &V[0]) || nlk_vec_create(c, &r)) return 1;      // the basis grows with the iteration (kdim 64 in the resolvent)
   auto apply = [&](const nlk_vec* in, nlk_vec* out) -> int {
     if (exptA_apply(op, in, out, transpose != 0)) return 1;
     if (minus_identity) { if (nlk_vec_axpby(-1.0, in, 1.0, out)) return 1; }
@@ -348,6 +357,7 @@ int nlk_gmres(nlk_op* op, int32_t minus_identity, const nlk_vec* b, nlk_vec* x, 
     std::vector<double> H((size_t)(kdim + 1) * kdim, 0.0), cs(kdim), sn(kdim), g(kdim + 1, 0.0), y(kdim);
     g[0] = beta; int kk = 0;
     for (int k = 0; k < kdim; ++k) {
+      if (!V[k + 1] && nlk_vec_create(c, &V[k + 1])) return 1;
       if (apply(V[k], V[k + 1])) return 1;
       if (c->prm.rst_mode != 1) vec_release_rst(V[k]);            // as in nlk_eigs: only the newest vector's rst fields are ever read
       std::vector<double> h(k + 1);
@@ -367,8 +377,6 @@ int nlk_gmres(nlk_op* op, int32_t minus_identity, const nlk_vec* b, nlk_vec* x, 
     if (basis_axpy(c, x, V.data(), kk, y.data())) return 1;
     x->nrst = nr;
   }
-  for (auto& v : V) nlk_vec_destroy(v);
-  nlk_vec_destroy(r);
   return 0;
 }
 
