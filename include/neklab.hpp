@@ -133,6 +133,74 @@ class exptA_linop {
   double tau_set_ = std::nan("");
 };
 
+// ---------------------------------------------------------------------------------------------------- nek_zvector / resolvent_linop
+// nek_zvector (src/vectors/neklab_vectors.f90:219-237): complex vector as a (re, im) pair of nek_dvector
+class nek_zvector {
+ public:
+  explicit nek_zvector(context& c) : re(c), im(c) {}
+  void zero() { re.zero(); im.zero(); }
+  void scal(std::complex<double> a) { check(nlk_zvec_scal(re.handle(), im.handle(), a.real(), a.imag()), "nek_zscal"); }
+  void axpby(std::complex<double> a, const nek_zvector& v, std::complex<double> b) {
+    check(nlk_zvec_axpby(a.real(), a.imag(), v.re.handle(), v.im.handle(), b.real(), b.imag(), re.handle(), im.handle()), "nek_zaxpby");
+  }
+  std::complex<double> dot(const nek_zvector& v) const {
+    double a = 0, b = 0; check(nlk_zvec_dot(re.handle(), im.handle(), v.re.handle(), v.im.handle(), &a, &b), "nek_zdot"); return {a, b};
+  }
+  nek_dvector re, im;
+};
+
+// resolvent_linop (src/linops/neklab_linops.f90:198-205; src/linops/resolvent.f90): components omega and baseflow
+class resolvent_linop {
+ public:
+  resolvent_linop(double omega_, const nek_dvector& baseflow) : omega(omega_), A_(1.0, baseflow) {}
+  void matvec(const nek_zvector& vec_in, nek_zvector& vec_out) { apply(vec_in, vec_out, false); }      // resolvent.f90:17-46
+  void rmatvec(const nek_zvector& vec_in, nek_zvector& vec_out) { apply(vec_in, vec_out, true); }      // :48-75
+  double omega;
+  double rtol = 0.0;                             // <= 0: the reference's GMRES tolerance 1e-6 (:122)
+  int info = 0;
+
+ private:
+  void apply(const nek_zvector& i, nek_zvector& o, bool adjoint) {
+    std::int32_t inf = 0;
+    check(nlk_resolvent_matvec(A_.handle(), omega, i.re.handle(), i.im.handle(), o.re.handle(), o.im.handle(), adjoint ? 1 : 0, rtol, &inf), "resolvent_matvec");
+    info = inf;
+  }
+  exptA_linop A_;
+};
+
+// ---------------------------------------------------------------------------------------------------- periodic orbits
+// nek_ext_dvector (src/vectors/real_extended_vectors.f90): nek_dvector + period T (dot adds T*T', :243; axpby combines T, :193)
+class nek_ext_dvector {
+ public:
+  explicit nek_ext_dvector(context& c, double T_ = 0.0) : vec(c), T(T_) {}
+  void zero() { vec.zero(); T = 0.0; }
+  void scal(double a) { vec.scal(a); T *= a; }
+  void axpby(double alpha, const nek_ext_dvector& v, double beta) { vec.axpby(alpha, v.vec, beta); T = beta * T + alpha * v.T; }
+  double dot(const nek_ext_dvector& v) const { return vec.dot(v.vec) + T * v.T; }
+  double norm() const { return std::sqrt(dot(*this)); }
+  std::int64_t get_size() const { return vec.get_size() + 1; }
+  nek_dvector vec;
+  double T;
+};
+
+// nek_upo_jacobian (src/systems/neklab_systems.f90:157-164; periodic_orbit.f90:46-181): linearisation about the orbit X = (X(0), T),
+// base flow and perturbation advanced together on the device
+class nek_upo_jacobian {
+ public:
+  nek_upo_jacobian(context& c, const nek_ext_dvector& X) : c_(&c), X_(&X) {}
+  void matvec(const nek_ext_dvector& vec_in, nek_ext_dvector& vec_out) { apply(vec_in, vec_out, false); }
+  void rmatvec(const nek_ext_dvector& vec_in, nek_ext_dvector& vec_out) { apply(vec_in, vec_out, true); }
+
+ private:
+  void apply(const nek_ext_dvector& i, nek_ext_dvector& o, bool transpose) {
+    double T = 0;
+    check(nlk_upo_jacobian(c_->handle(), X_->vec.handle(), X_->T, i.vec.handle(), i.T, o.vec.handle(), &T, transpose ? 1 : 0), "nek_upo_jacobian");
+    o.T = T;
+  }
+  context* c_;
+  const nek_ext_dvector* X_;
+};
+
 // ---------------------------------------------------------------------------------------------------- analysis drivers
 struct eigs_result {
   std::vector<std::complex<double>> mu;        // Ritz values of exp(tau L)
