@@ -271,6 +271,7 @@ module neklab_b200
 
    public :: nek2vec, vec2nek, linear_stability_analysis_fixed_point, transient_growth_analysis_fixed_point
    public :: newton_fixed_point_iteration, set_neklab_forcing, get_neklab_forcing, zero_neklab_forcing, zero_neklab_forcing_ipert
+   public :: resolvent_apply, upo_jacobian_apply
 
 contains
 
@@ -489,6 +490,36 @@ contains
       mode = 1; if (present(tol_mode)) mode = int(tol_mode, c_int32_t)
       call check(nlk_newton_fixed_point(nlk_ctx, tau, bf%h, tol, mode, 40_c_int32_t, 30_c_int32_t, hist, niter, i4), 'newton_fixed_point_iteration')
       info = int(i4)
+   end subroutine
+
+   ! ---- resolvent_linop%matvec / %rmatvec (src/linops/resolvent.f90:17-75): the nek_zvector is passed as its (re, im) nek_dvector pair
+   subroutine resolvent_apply(A, omega, f_re, f_im, out_re, out_im, adjoint, info)
+      type(exptA_linop), intent(inout) :: A                              ! supplies the base flow (self%baseflow of resolvent_linop)
+      real(dp), intent(in) :: omega
+      type(nek_dvector), intent(in) :: f_re, f_im
+      type(nek_dvector), intent(inout) :: out_re, out_im
+      logical, intent(in) :: adjoint
+      integer, intent(out) :: info
+      integer(c_int32_t) :: i4, adj
+      call ensure(out_re); call ensure(out_im)
+      adj = 0; if (adjoint) adj = 1
+      call check(nlk_resolvent_matvec(A%h, omega, f_re%h, f_im%h, out_re%h, out_im%h, adj, 0.0_c_double, i4), 'resolvent_matvec')
+      info = int(i4)
+   end subroutine
+
+   ! ---- nek_upo_jacobian%matvec / %rmatvec (src/systems/periodic_orbit.f90:46-181): nek_ext_dvector = (nek_dvector, T)
+   subroutine upo_jacobian_apply(X, T_X, vec_in, T_in, vec_out, T_out, transpose)
+      type(nek_dvector), intent(in) :: X, vec_in
+      real(dp), intent(in) :: T_X, T_in
+      type(nek_dvector), intent(inout) :: vec_out
+      real(dp), intent(out) :: T_out
+      logical, intent(in) :: transpose
+      integer(c_int32_t) :: tr
+      real(c_double) :: t
+      call ensure(vec_out)
+      tr = 0; if (transpose) tr = 1
+      call check(nlk_upo_jacobian(nlk_ctx, X%h, T_X, vec_in%h, T_in, vec_out%h, t, tr), 'jac_direct_map')
+      T_out = t
    end subroutine
 
    ! ---- forcing registry (src/neklab_nek_forcing.f90)
