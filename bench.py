@@ -190,6 +190,8 @@ def cpu_sample(workload, nsteps, nwarm, half_width=6.0):
     from oracle.mesh import SEMesh
     from oracle.precond import SchwarzCoarse
     from oracle.stepper import NekVec, StepParams
+    from oracle.cref import CRef
+    CRef.use_all_cores()                                  # under torchrun the workers inherit OMP_NUM_THREADS=1
     case = cylinder_inputs()
     if workload == "cylinder":
         om = SEMesh(case["coords"], case["vertex"], case["cbc"], 9)

@@ -633,6 +633,7 @@ void nekref_reset_history(void* h) {
 void nekref_advance(void* h, int istep) { advance(*(Ref*)h, istep); }
 void nekref_counters(void* h, int64_t* cg, int64_t* gm) { Ref* R = (Ref*)h; *cg = R->cg_iters; *gm = R->gm_iters; }
 int nekref_threads() { return omp_get_max_threads(); }
+void nekref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }     // torchrun exports OMP_NUM_THREADS=1 to its workers
 // operator-level hooks (validated against the numpy oracle in tests/test_oracle_cpp.py)
 void nekref_axhelm(void* h, const double* u, double h1, double h2, double* w) { axhelm(*(Ref*)h, u, w, h1, h2); }
 void nekref_dssum(void* h, double* u) { dssum(*(Ref*)h, u); }

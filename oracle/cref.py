@@ -144,6 +144,13 @@ class CRef:
     def pressure(self, rhs, tol):
         rhs = _c(rhs); x = np.zeros_like(rhs); it = lib().nekref_pressure(self.h, _p(rhs), C.c_double(tol), _p(x)); return x, it
 
+    @staticmethod
+    def use_all_cores():
+        """Let the C++ oracle use every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        lib().nekref_set_threads(C.c_int(n))
+        return n
+
     def threads(self):
         return int(lib().nekref_threads())
 
