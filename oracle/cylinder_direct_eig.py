@@ -1,4 +1,4 @@
-"""ORACLE-side study (test infrastructure, CPU only): the leading eigenvalue of the SEMI-DISCRETE linearised operator of the
+"""ORACLE (test infrastructure, CPU only; never imported by the product): the leading eigenvalue of the SEMI-DISCRETE linearised operator of the
 cylinder case (examples/cylinder/stability/direct: Re = 50, lx1 = 6, lxd = 9, the shipped base flow) by a direct sparse
 shift-invert eigen-solve -- no time stepper involved.
 
@@ -9,7 +9,7 @@ restatement (1.01573, tests/golden/cylinder_golden_sweep_r02.json) independently
 solver and the Krylov-Schur driver, and says where the reference's golden 1.0156 +- 1e-4 (test/neklabTests.py:42-46) sits
 relative to it.
 
-    python examples/cylinder_direct_eig.py [--out tests/golden/cylinder_direct_eig.json]
+    python -m oracle.cylinder_direct_eig [--out tests/golden/cylinder_direct_eig.json]
 """
 import argparse
 import json

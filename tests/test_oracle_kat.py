@@ -142,7 +142,7 @@ def test_golden_sweep_record():
 
 
 def test_direct_eigenvalue_record():
-    """tests/golden/cylinder_direct_eig.json (examples/cylinder_direct_eig.py): the leading eigenvalue of the SEMI-DISCRETE
+    """tests/golden/cylinder_direct_eig.json (oracle/cylinder_direct_eig.py): the leading eigenvalue of the SEMI-DISCRETE
     linearised operator on the reference's cylinder mesh and base flow by a direct sparse shift-invert solve (no time stepper).
     The time-stepped Ritz values of the sweep converge onto it -- consistent rst at CFL 0.5 is 6.5e-5 away, dt/2 closer -- and it
     sits 2.7e-5 above the golden's acceptance window: DESIGN.md 1.1 item 3a."""
@@ -165,7 +165,7 @@ def test_direct_eigenvalue_recomputed(tmp_path):
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = tmp_path / "eig.json"
-    r = subprocess.run([sys.executable, os.path.join(root, "examples", "cylinder_direct_eig.py"), "--out", str(out)], capture_output=True, text=True, timeout=1800)
+    r = subprocess.run([sys.executable, os.path.join(root, "oracle", "cylinder_direct_eig.py"), "--out", str(out)], capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0, r.stderr[-2000:]
     a = json.load(open(out)); b = json.load(open(os.path.join(GOLDEN, "cylinder_direct_eig.json")))
     assert abs(complex(*a["lambda"][0]) - complex(*b["lambda"][0])) < 1e-9
