@@ -27,7 +27,19 @@ from oracle.stepper import _local_deriv_blocks  # noqa: E402
 from tests.util import cylinder_case  # noqa: E402
 
 
-def assemble(om, U, nu, rho=1.0):
+def conv_collocated(om, u, C):
+    """un-dealiased alternative (Nek `conv1`, param(99) = 0): bm1 * (C . grad u) evaluated at the GLL points"""
+    g = ops.local_grad(om, u)                               # d u / d r_k
+    d = om.ndim
+    out = 0.0
+    for c in range(d):
+        dudx = sum(om.rx[k][c] * g[k] for k in range(d)) / om.jac
+        out = out + C[c] * dudx
+    return om.bm1 * out
+
+
+def assemble(om, U, nu, rho=1.0, conv=None):
+    conv = conv or ops.convect_new
     d, E = om.ndim, om.E
     nn, nq = om.n ** d, om.q ** d
     shape = om.bm1.shape
@@ -44,9 +56,9 @@ def assemble(om, U, nu, rho=1.0):
         for cj in range(d):
             up = [zero] * d; up = list(up); up[cj] = eb
             for c in range(d):
-                r = rho * ops.convect_new(om, U[c], up)                            # u'.grad U_c
+                r = rho * conv(om, U[c], up)                                       # u'.grad U_c
                 if c == cj:
-                    r = r + rho * ops.convect_new(om, eb, U) + ops.axhelm(om, eb, nu, 0.0)
+                    r = r + rho * conv(om, eb, U) + ops.axhelm(om, eb, nu, 0.0)
                 blk[c][cj][:, :, b] = r.reshape(E, nn)
     bsr = lambda B_: sp.bsr_matrix((B_, np.arange(E), np.arange(E + 1)), shape=(E * nn, E * nn)).tocsr()
     K = [[(Q.T @ bsr(blk[c][cj]) @ Q).tocsr()[free[c]][:, free[cj]] for cj in range(d)] for c in range(d)]
@@ -60,10 +72,11 @@ def assemble(om, U, nu, rho=1.0):
 
 def main():
     ap = argparse.ArgumentParser(); ap.add_argument("--out", default=None); ap.add_argument("--nev", type=int, default=4)
+    ap.add_argument("--conv", default="dealiased", choices=["dealiased", "collocated"], help="sensitivity study: un-dealiased convective terms")
     a = ap.parse_args()
     t0 = time.time()
     om, bf, prm, _ = cylinder_case()
-    K, Bg, D, free = assemble(om, bf.v, prm.viscosity)
+    K, Bg, D, free = assemble(om, bf.v, prm.viscosity, conv=conv_collocated if a.conv == "collocated" else None)
     nf = [len(f) for f in free]; nu_ = sum(nf); n2 = om.bm2.size
     Kf = sp.bmat([[K[0][0], K[0][1]], [K[1][0], K[1][1]]]).tocsr()
     Df = sp.hstack(D).tocsr()
@@ -81,7 +94,7 @@ def main():
     lam = lam[order]; V = V[:, order]
     res = [float(np.linalg.norm(A @ V[:, i] - lam[i] * (M @ V[:, i])) / np.linalg.norm(V[:, i])) for i in range(len(lam))]
     mu = np.exp(lam)                                        # tau = 1
-    out = {"case": "cylinder Re=50, lx1=6, lxd=9, shipped base flow (tests/golden/cylinder_case.npz)", "unknowns": [int(nu_), int(n2)],
+    out = {"case": "cylinder Re=50, lx1=6, lxd=9, shipped base flow (tests/golden/cylinder_case.npz)", "convection": a.conv, "unknowns": [int(nu_), int(n2)],
            "shift": [sigma0.real, sigma0.imag], "lambda": [[float(z.real), float(z.imag)] for z in lam], "residuals": res,
            "exp_lambda_modulus": [float(abs(z)) for z in mu], "exp_lambda": [[float(z.real), float(z.imag)] for z in mu],
            "seconds": time.time() - t0}

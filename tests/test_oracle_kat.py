@@ -150,6 +150,7 @@ def test_direct_eigenvalue_record():
     mu = complex(*d["exp_lambda"][0]); lam = complex(*d["lambda"][0])
     assert d["residuals"][0] < 1e-12 and abs(np.exp(lam) - mu) < 1e-14
     assert abs(abs(mu) - 1.0157273) < 1e-6
+    assert all(abs(v["exp_lambda_modulus"] - abs(mu)) < 1e-6 for v in d["sensitivity"].values())      # un-dealiased convection: same value
     rec = json.load(open(os.path.join(GOLDEN, "cylinder_golden_sweep_r02.json")))
     cons = [r for r in rec if r["rst_mode"] == 1 and r["step_variant"] == 0 and r["torder"] == 3 and r["cfl"] == 0.5][0]
     assert abs(complex(cons["lam_re"], cons["lam_im"]) - mu) < 7e-5                      # whole temporal error of the stepper at CFL 0.5
