@@ -91,6 +91,18 @@ def cylinder_inputs():
     return dict(coords=z["coords"], vertex=z["vertex"], cbc=z["cbc"], vel=z["vel"], pr=z["pr"], pid=z["pid"])
 
 
+def zslab_partition(E2, L, world):
+    """Strong-scaling partition of the extruded mesh: z-slabs of whole 2-D layers (uneven when world does not divide L).
+    Returns (layer bounds per rank, element -> rank map or None for one rank)."""
+    bounds = np.linspace(0, L, world + 1).round().astype(int)
+    if world <= 1:
+        return bounds, None
+    gllnid = np.zeros(E2 * L, dtype=np.int32)
+    for r in range(world):
+        gllnid[E2 * bounds[r]:E2 * bounds[r + 1]] = r
+    return bounds, gllnid
+
+
 def extrude(case, n, layers_total, lz_per_layer=0.5, layer_range=None):
     """Extrude the 2-D cylinder mesh (bilinear re-interpolation to lx1=n) into `layers_total` periodic z-layers (>= 3: with two
     layers the vertical edges of both layers would carry the same vertex pair).  Connectivity (vertex ids, boundary codes) is
@@ -334,14 +346,9 @@ def native_arm(workload, steps, warmup, a, rank, world, local):
         cfg = synth_config(a, world)
         L = cfg["layers_total"]
         E2 = case["coords"].shape[0]
-        bounds = np.linspace(0, L, world + 1).round().astype(int)          # z-slabs of whole layers (uneven when world does not divide L)
+        bounds, gllnid = zslab_partition(E2, L, world)
         l0, l1 = int(bounds[rank]), int(bounds[rank + 1])
         coords, Uall, vertex, cbc = extrude(case, 8, L, layer_range=(l0, l1))
-        gllnid = None
-        if world > 1:
-            gllnid = np.zeros(E2 * L, dtype=np.int32)
-            for r in range(world):
-                gllnid[E2 * bounds[r]:E2 * bounds[r + 1]] = r
         t_setup = time.perf_counter()
         mesh = api.Mesh(coords, vertex, cbc, 12, gllnid=gllnid, rank=rank, nranks=world)
         prm = api.default_params(viscosity=1.0 / 50.0, torder=3, vtol=1e-9, ptol=1e-7, pr_proj=20, coarse_iters=a.coarse_iters)

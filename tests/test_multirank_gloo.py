@@ -68,3 +68,65 @@ def test_partitioned_dssum_matches_single_rank(nlk_lib, world):
         p.join(timeout=60)
     assert all(ok for _, ok, _, _ in res), res
     assert all(nn >= 1 for _, _, nn, _ in res)
+
+
+def _worker_zslab(rank, world, port, q):
+    """The strong-scaling layout of bench.py: z-slabs of a periodic extruded mesh (every rank generates only its own layers)."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import bench
+    from neklab_b200 import api
+    from oracle.mesh import SEMesh
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L, n = 8, 4
+    case = bench.window_case(bench.cylinder_inputs(), 2.0)
+    E2 = case["coords"].shape[0]
+    bounds, gllnid = bench.zslab_partition(E2, L, world)
+    l0, l1 = int(bounds[rank]), int(bounds[rank + 1])
+    coords, _, vertex, cbc = bench.extrude(case, n, L, layer_range=(l0, l1))
+    full, _, _, _ = bench.extrude(case, n, L)
+    om = SEMesh(full, vertex, cbc, 6)
+    sel = np.where(gllnid == rank)[0]
+    assert np.array_equal(full[sel], coords)                        # the rank's own layers, in global element order
+    m = api.Mesh(coords, vertex, cbc, 6, gllnid=gllnid, rank=rank, nranks=world)
+    glo = m.glo_num()
+    u_all = np.random.default_rng(7).integers(-50, 50, size=om.bm1.shape).astype(np.float64)
+    uq, inv = np.unique(glo.ravel(), return_inverse=True)
+    s = np.bincount(inv, weights=u_all[sel].ravel())
+    nbs = m.neighbors()
+    recv = {}; reqs = []
+    for r, gids in nbs:
+        pos = np.searchsorted(uq, gids)
+        assert np.array_equal(uq[pos], gids)
+        buf = torch.zeros(len(gids), dtype=torch.float64)
+        recv[r] = (pos, buf)
+        reqs.append(dist.isend(torch.from_numpy(s[pos].copy()), dst=r)); reqs.append(dist.irecv(buf, src=r))
+    for rq in reqs:
+        rq.wait()
+    for r in sorted(recv):
+        pos, buf = recv[r]
+        np.add.at(s, pos, buf.numpy())
+    ok = bool(np.array_equal(s[inv].reshape(u_all[sel].shape), om.dssum(u_all)[sel]))
+    want = sorted({(rank - 1) % world, (rank + 1) % world} - {rank})      # periodic in z: the first and the last slab are neighbours
+    q.put((rank, ok and sorted(r for r, _ in nbs) == want, len(nbs), [int(b) for b in bounds]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_zslab_partition_exchange_plan(nlk_lib, world):
+    """bench.py's strong-scaling partition (uneven slabs for world = 3, one layer per rank for world = 8, periodic wrap)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_zslab, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in res), res
+    assert sum(1 for _ in res) == world and res[0][3][-1] == 8 and res[0][3][0] == 0
