@@ -706,7 +706,7 @@ int nlk_nonlinear_map(nlk_ctx* c, double tau, double cfl_limit, const nlk_vec* i
 int nlk_newton_fixed_point(nlk_ctx* c, double tau, nlk_vec* X, double tol, int32_t tol_mode, int32_t maxiter, int32_t gmres_kdim,
                            double* rnorm_hist, int32_t* niter, int32_t* info) {
   const double mintol = 10.0 * 1e-15, maxtol = 1.0e-4;
-  const double vtol0 = c->prm.vtol, ptol0 = c->prm.ptol, cfl0 = c->prm.cfl_limit;
+  const double vtol0 = c->prm.vtol, ptol0 = c->prm.ptol, ttol0 = c->prm.ttol, cfl0 = c->prm.cfl_limit;
   nlk_vec *r = nullptr, *dx = nullptr; nlk_op* J = nullptr;
   if (nlk_vec_create(c, &r) || nlk_vec_create(c, &dx) || nlk_exptA_create(c, tau, X, &J)) return 1;
   double tol_s = std::max(tol, mintol);
@@ -719,14 +719,14 @@ int nlk_newton_fixed_point(nlk_ctx* c, double tau, nlk_vec* X, double tol, int32
       if (t < 10 * target) t = target;
       tol_s = std::min(t, maxtol);
     }
-    c->prm.vtol = tol_s * 0.1; c->prm.ptol = tol_s * 0.1;          // nonlinear_map: vtol = ptol = atol*0.1
+    c->prm.vtol = tol_s * 0.1; c->prm.ptol = tol_s * 0.1; c->prm.ttol = c->prm.vtol;          // nonlinear_map: vtol = ptol = atol*0.1 (restol(:) = vtol)
     if ((rc = nlk_nonlinear_map(c, tau, 0.4, X, r))) break;
     double rn; if ((rc = nlk_vec_norm(r, &rn))) break;
     rnorm_hist[it] = rn;
     if (rn < tol) { *info = 0; break; }
     if (it == maxiter) break;
     // Jacobian = exptA(X) - I with vtol = ptol = atol*0.5, cfl 0.5
-    c->prm.vtol = tol_s * 0.5; c->prm.ptol = tol_s * 0.5; c->prm.cfl_limit = 0.5;
+    c->prm.vtol = tol_s * 0.5; c->prm.ptol = tol_s * 0.5; c->prm.ttol = c->prm.vtol; c->prm.cfl_limit = 0.5;
     if ((rc = nlk_exptA_set_baseflow(J, X))) break;
     if ((rc = nlk_vec_zero(dx))) break;
     int ginfo = 0;
@@ -736,7 +736,7 @@ int nlk_newton_fixed_point(nlk_ctx* c, double tau, nlk_vec* X, double tol, int32
     X->nrst = nr;
   }
   *niter = it;
-  c->prm.vtol = vtol0; c->prm.ptol = ptol0; c->prm.cfl_limit = cfl0;
+  c->prm.vtol = vtol0; c->prm.ptol = ptol0; c->prm.ttol = ttol0; c->prm.cfl_limit = cfl0;
   nlk_exptA_destroy(J); nlk_vec_destroy(r); nlk_vec_destroy(dx);
   return rc;
 }
